@@ -1,0 +1,161 @@
+"""
+Pins the oracle (oracle/asl_models.py) to the golden vectors produced by running the
+unmodified reference source (tests/golden/make_golden.py).  Tolerance: the goldens and
+the oracle are both float64, so agreement is required to 1e-12 relative to the case's
+peak signal; boundary elements whose mask differs only through fp64 rounding are not
+expected (inputs are float32-representable).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import asl_models as om
+
+TIS = [2.05, 2.3, 2.55, 2.8, 3.05, 3.3]
+
+CASE_CFG = {
+    "casl_tiss": dict(casl=True),
+    "pasl_tiss": dict(casl=False),
+    "casl_tiss_art": dict(casl=True, inferart=True),
+    "pasl_tiss_art": dict(casl=False, inferart=True),
+    "casl_noatt": dict(casl=True, inferatt=False),
+    "casl_artonly": dict(casl=True, artonly=True),
+    "casl_t1": dict(casl=True, infert1=True),
+    "pasl_t1_art": dict(casl=False, infert1=True, inferart=True),
+    "casl_pvc": dict(casl=True, incwm=True, inferwm=True, inferart=True, pc=0.98),
+    "casl_pvc_t1": dict(casl=True, incwm=True, inferwm=True, infert1=True, pc=0.98),
+}
+
+
+def _cfg(case, rec):
+    kw = dict(CASE_CFG[case])
+    for k in ("pvgm", "pvwm"):
+        if k in rec:
+            kw[k] = rec[k]
+    return om.AslConfig(tau=1.8, t1b=1.65, **kw)
+
+
+@pytest.mark.parametrize("case", sorted(CASE_CFG))
+def test_aslrest_evaluate_matches_reference_source(golden, case):
+    rec = golden("aslrest_eval")[case]
+    cfg = _cfg(case, rec)
+    assert cfg.param_names() == list(rec["names"])                       # aslrest.py:183-246 order
+    assert float(rec["pc"]) == pytest.approx(float(np.mean(cfg.pc)))     # aslrest.py:131-135
+    params = [torch.as_tensor(p, dtype=torch.float64) for p in rec["params"]]
+    t = torch.as_tensor(rec["t"], dtype=torch.float64)
+    out = om.evaluate(cfg, params, t).numpy()
+    scale = np.abs(rec["out64"]).max()
+    # with a fixed ATT the reference evaluates tau+att and exp(-att/t1b) on float32 node arrays
+    # (aslrest.py:157,279,362,371), so its "float64" run is only float32-accurate in those terms
+    tol = 1e-12 if cfg.inferatt else 3e-7
+    assert np.abs(out - rec["out64"]).max() <= tol * scale
+    # the reference's own float32 evaluation stays within 1e-5 of the float64 one away from mask edges
+    close = np.abs(rec["out32"] - rec["out64"]) <= 2e-5 * scale
+    assert close.mean() > 0.995
+
+
+def test_reference_defects_are_recorded(golden):
+    g = golden("aslrest_eval")
+    # inferart without inferatt reads a parameter that does not exist
+    assert str(g["casl_art_noatt"]["error"]) == "IndexError"
+    # incwm without inferwm hands a float to tissue_signal (aslrest.py:292,328,352)
+    assert str(g["casl_incwm_fixed"]["error"]) == "AttributeError"
+    # the oracle implements the documented intent for both
+    cfg = om.AslConfig(casl=True, inferart=True, inferatt=False)
+    assert cfg.param_names() == ["ftiss", "fblood"]
+    t = torch.tensor([[[2.0, 3.0]]], dtype=torch.float64)
+    out = om.evaluate(cfg, [torch.full((1, 1, 1), 10.0, dtype=torch.float64),
+                            torch.full((1, 1, 1), 5.0, dtype=torch.float64)], t)
+    assert out.shape == (1, 1, 2) and torch.isfinite(out).all()
+
+
+def test_priors_and_dists_from_reference_init(golden):
+    g = golden("aslrest_eval")["casl_tiss_art"]
+    assert list(g["prior_types"]) == ["N", "N", "A", "N"]                # aslrest.py:237
+    np.testing.assert_allclose(g["prior_mean"], [1.5, 1.3, 0.0, 1.0], rtol=1e-6)
+    np.testing.assert_allclose(g["prior_var"], [1e6, 1.0, 1e6, 1.0], rtol=1e-6)
+    np.testing.assert_allclose(g["post_var"], [1.5, 1.0, 1.5, 1.0], rtol=1e-6)
+    assert float(g["artt"]) == pytest.approx(1.0)                        # att - 0.3 (aslrest.py:86-87)
+
+
+def test_edges_and_quick_test(golden):
+    g = golden("aslrest_edges")
+    cfg = om.AslConfig(casl=True, inferart=True, tau=1.8, t1b=1.65)
+    e = g["edges"]
+    out = om.evaluate(cfg, [torch.as_tensor(p, dtype=torch.float64) for p in e["params"]],
+                      torch.as_tensor(e["t"], dtype=torch.float64)).numpy()
+    assert np.isfinite(out).all()
+    np.testing.assert_allclose(out, e["out64"], rtol=0, atol=1e-12 * np.abs(e["out64"]).max())
+    q = g["quick_test"]
+    cfgq = om.AslConfig(casl=True, tau=1.8, t1b=1.6, t1=1.3)
+    outq = om.evaluate(cfgq, [torch.as_tensor(p, dtype=torch.float64) for p in q["params"]],
+                       torch.as_tensor(q["t"], dtype=torch.float64)).numpy()
+    np.testing.assert_allclose(outq, q["out64"], rtol=1e-13)
+    # SURVEY Appendix D1 (fp64 restatement, quick_test.py configuration)
+    d1 = [0.503872642, 0.616141242, 0.708511842, 0.784511077, 0.847040537, 0.734146299]
+    np.testing.assert_allclose(outq[0, 0], d1, rtol=2e-7)   # golden inputs are float32-rounded
+    np.testing.assert_allclose(outq[2, 0], 10 * outq[0, 0], rtol=1e-12)
+
+
+def test_tpts_matches_reference_on_real_mask(golden):
+    import os
+    sdir = "/root/reference/scripts"
+    g = golden("aslrest_real")["real"]
+    if not os.path.isdir(sdir):
+        pytest.skip("reference data only exists in the build container")
+    from svb_models_asl_b200.svbcompat import DataModel
+    dm = DataModel(os.path.join(sdir, "asldata_diff.nii.gz"), mask=os.path.join(sdir, "asldata_mask.nii.gz"))
+    assert dm.n_nodes == int(g["n_nodes"]) == 33222
+    plds = [0.25, 0.5, 0.75, 1.0, 1.25, 1.5]
+    t = om.tpts([1.8 + p for p in plds], 8, dm.shape, dm.mask_vol, slicedt=0.0452)
+    np.testing.assert_array_equal(t[g["sel"]], g["tpts_sel"])
+    assert float(t.astype(np.float64).sum()) == pytest.approx(float(g["tpts_sum"]), rel=1e-12)
+
+
+def test_disp_pieces_match_reference_source(golden):
+    d = golden("disp_pieces")["disp"]
+    cfg = om.AslConfig(casl=True, inferart=True, disp=True, tau=1.8, t1b=1.65, conv_tmax=float(d["conv_tmax"]))
+    grid, nt = om.disp_grid(cfg)
+    assert nt == int(d["conv_nt"]) == 51                                  # aslrest_disp.py:41-43
+    np.testing.assert_allclose(grid.numpy(), d["conv_t"], atol=1e-15)
+    assert list(d["names"]) == cfg.param_names()
+    np.testing.assert_allclose(d["prior_mean"][-2:], np.log([7.4, 0.74]), rtol=1e-6)   # LogNormal geom
+    delt, s, sp = (torch.as_tensor(d[k], dtype=torch.float64) for k in ("delt", "s", "sp"))
+    cfg_w = om.AslConfig(casl=True, disp=True, disp_postbolus="as_written", tau=1.8, t1b=1.65)
+    aif = om.aif_gammadisp(cfg_w, grid, delt, s, sp)
+    np.testing.assert_allclose(aif.numpy(), d["aif_as_written"], rtol=1e-12, atol=1e-14)
+    # resid_wellmix divides by float32 node arrays (aslrest_disp.py:145 with aslrest.py:176-178)
+    t1app = om.t1_apparent(cfg, 1.3, 0.9, 0.01, grid)[0]
+    resid = torch.exp(-grid / t1app)
+    np.testing.assert_allclose(resid.numpy(), d["resid"], rtol=1e-7)
+    resid = torch.as_tensor(d["resid"])
+    curve = torch.as_tensor(d["curve"])
+    np.testing.assert_allclose(om.conv_causal(curve, resid, 0.1).numpy(), d["conv_of_curve"], rtol=1e-12)
+    np.testing.assert_allclose(om.conv_causal(aif, resid, 0.1).numpy(), d["conv_of_aif"], rtol=1e-12, atol=1e-14)
+    t = torch.as_tensor(d["t"])
+    np.testing.assert_allclose(om.interp_grid(t, 5.0, curve).numpy(), d["interp_of_curve"], rtol=1e-12)
+    np.testing.assert_allclose(om.aif_gammadisp(cfg_w, t, delt, s, sp).numpy(), d["aif_at_t_as_written"],
+                               rtol=1e-12, atol=1e-14)
+    # O(NT) recurrence == the 101-tap correlation
+    rho = float(resid[1])
+    c = torch.zeros_like(curve)
+    c[..., 0] = 0.1 * curve[..., 0]
+    for i in range(1, curve.shape[-1]):
+        c[..., i] = rho * c[..., i - 1] + 0.1 * curve[..., i]
+    np.testing.assert_allclose(c.numpy(), d["conv_of_curve"], rtol=1e-11)
+    # intended post-bolus term differs from the as-written zero exactly where t > delt + tau
+    aif_int = om.aif_gammadisp(cfg, grid, delt, s, sp)
+    post = (grid > delt + 1.8)
+    assert torch.all(aif_int[~post.expand_as(aif_int)] == aif[~post.expand_as(aif)])
+    assert (aif_int[post.expand_as(aif_int)] > 0).any()
+
+
+def test_nn_matches_reference_source(golden):
+    n = golden("aslnn_eval")["nn"]
+    assert list(n["names"]) == ["ftiss", "delttiss"] and list(n["dists"]) == ["LogNormal", "FoldedNormal"]
+    ws = [n["w%i" % i] for i in range(3)]
+    bs = [n["b%i" % i] for i in range(3)]
+    f, dl = (torch.as_tensor(p, dtype=torch.float64) for p in n["params"])
+    out = om.evaluate_nn(ws, bs, f, dl, torch.as_tensor(n["t"], dtype=torch.float64)).numpy()
+    np.testing.assert_allclose(out, n["out64"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(n["tpts_default"], [TIS], rtol=1e-12)     # aslnn.py:139-141 (slicedt == 0)
