@@ -1,0 +1,205 @@
+/*
+ * svbasl.h - C ABI of libsvbasl.so: B200 (sm_100a) kernels for the ASL
+ * stochastic-variational-Bayes hot path of physimals/svb_models_asl.
+ *
+ * The reference exposes NO native interface for this path - it is a Python
+ * plugin (entry-point group `svb.models`, /root/reference/setup.py:89-95) whose
+ * arithmetic runs inside TensorFlow.  Each entry point below therefore cites
+ * the reference *Python* interface whose work it takes over; the binding a
+ * maintainer adds on the reference side is the ctypes stub in INTEGRATION.md
+ * (mirrored by svb_models_asl_b200/_lib.py).
+ *
+ * Conventions
+ *  - plain C, no torch / C++ types; return 0 on success, a negative
+ *    SVBASL_E_* code otherwise; svbasl_last_error() gives the message
+ *    (thread-local).  Nothing throws across the boundary.
+ *  - the caller owns every buffer; device pointers unless the name says host.
+ *    The library allocates nothing persistent (svbasl_step_host owns a small
+ *    staging context created/destroyed explicitly).
+ *  - all launches are asynchronous on the caller's `stream` (a cudaStream_t
+ *    passed as void*; NULL = legacy default stream).
+ *  - device arrays are SoA, voxel-fastest: a [K][W] array has row stride `ld`
+ *    floats (ld >= n_vox), element (k, w) at base[k*ld + w].
+ */
+#ifndef SVBASL_H
+#define SVBASL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVBASL_ABI_VERSION 1
+#define SVBASL_MAX_PAR 10          /* P' = model parameters + noise */
+#define SVBASL_MAX_SPATIAL 4
+
+/* error codes */
+#define SVBASL_OK 0
+#define SVBASL_E_INVALID (-1)      /* bad argument / inconsistent descriptor */
+#define SVBASL_E_UNSUPPORTED (-2)  /* combination not compiled into the library */
+#define SVBASL_E_CUDA (-3)         /* CUDA runtime error (message has the detail) */
+
+/* model kinds: the three `svb.models` entry points (setup.py:91-93) */
+#define SVBASL_MODEL_ASLREST 0     /* svb_models_asl/aslrest.py  AslRestModel */
+#define SVBASL_MODEL_ASLREST_DISP 1/* svb_models_asl/aslrest_disp.py AslRestDisp */
+#define SVBASL_MODEL_ASLNN 2       /* svb_models_asl/aslnn.py AslNNModel */
+
+/* model flags (aslrest.py:24-67 options after resolution in __init__ :69-246) */
+#define SVBASL_F_CASL 0x01         /* casl */
+#define SVBASL_F_INFERATT 0x02     /* inferatt: delttiss (/deltwm/deltblood) are parameters */
+#define SVBASL_F_INFERART 0x04     /* inferart: fblood (+deltblood) */
+#define SVBASL_F_INCWM 0x08        /* incwm: add a WM tissue component */
+#define SVBASL_F_INFERWM 0x10      /* inferwm: fwm (+deltwm) are parameters (implies INCWM) */
+#define SVBASL_F_INFERT1 0x20      /* infert1: t1 (+t1wm) are parameters */
+#define SVBASL_F_ARTONLY 0x40      /* artonly: no tissue component */
+#define SVBASL_F_DISP_INFER 0x80   /* aslrest_disp infer_disp_params: s, sp are parameters */
+#define SVBASL_F_DISP_ASWRITTEN 0x100 /* reproduce gamma2-gamma2 == 0 (aslrest_disp.py:108) */
+
+/* parameter transforms (svb dist: Normal / LogNormal / FoldedNormal) */
+#define SVBASL_XF_IDENTITY 0
+#define SVBASL_XF_EXP 1
+#define SVBASL_XF_ABS 2
+
+/* prior types (get_parameter(prior_type=...), aslrest.py:237) */
+#define SVBASL_PRIOR_N 0           /* fixed Normal */
+#define SVBASL_PRIOR_ARD 1         /* "A": Normal with trainable per-voxel log precision */
+#define SVBASL_PRIOR_MRF 2         /* "M": spatial Laplacian prior with trainable global log ak */
+
+/* latent-loss form */
+#define SVBASL_LATENT_NUMERIC 0    /* force_num_latent_loss=True (asl_example.py:41) */
+#define SVBASL_LATENT_ANALYTIC 1   /* closed-form Gaussian KL */
+
+/* Resolved model options: what AslRestModel/AslRestDisp/AslNNModel.__init__ compute
+ * (aslrest.py:69-246, aslrest_disp.py:30-43, aslnn.py:61-88), as a flat POD. */
+typedef struct svbasl_model {
+    int32_t kind;                  /* SVBASL_MODEL_* */
+    uint32_t flags;                /* SVBASL_F_* */
+    float tau, t1b;                /* aslrest.py:27,50 */
+    float t1, pc, fcalib, att;     /* GM tissue constants (aslrest.py:35-39,131-135) */
+    float t1wm, pcwm, fcalibwm, attwm, fwm;   /* WM constants (aslrest.py:42-47) */
+    float artt;                    /* arterial arrival time when not inferred (aslrest.py:86-87) */
+    float leadscale;               /* aslrest.py:232 */
+    float pvgm_s, pvwm_s;          /* partial volumes when uniform ... */
+    const float *pvgm, *pvwm;      /* ... or per voxel [n_vox] (aslrest.py:110-114); NULL = use scalar */
+    /* aslrest_disp.py:24-43 */
+    float conv_dt, conv_tmax;
+    int32_t conv_nt;
+    float s_fixed, sp_fixed;       /* used when !DISP_INFER (aslrest_disp.py:88-90) */
+    /* aslnn.py:229-241: 2->10 tanh ->10 tanh ->1, packed W0[2][10] b0[10] W1[10][10] b1[10] W2[10] b2[1] */
+    const float *nn_weights;       /* device, 151 floats */
+} svbasl_model;
+
+/* Inference-engine description for one shard of voxels: what svb's SvbFit builds around the
+ * plugin (posterior, noise, priors, loss). */
+typedef struct svbasl_engine {
+    int64_t n_vox;                 /* voxels this call processes: local indices [w_begin, w_begin + n_vox) */
+    int64_t w_begin;               /* first local index processed (= size of the lower halo; 0 without halos) */
+    int64_t ld;                    /* row stride of every [K][W] array, floats (>= w_begin + n_vox + upper halo) */
+    int64_t vox_offset;            /* global index of LOCAL index 0 (RNG stream: draws depend on the global
+                                      voxel only, so results do not depend on the sharding) */
+    int64_t n_vox_global;          /* voxels in the whole volume */
+    int32_t n_par;                 /* P' = model parameters + noise (must match the model) */
+    int32_t n_samples;             /* S  (sample_size, asl_example.py:31) */
+    int32_t n_batch;               /* B  time points per iteration (batch_size, asl_example.py:30) */
+    int32_t t_full;                /* T  total time points (likelihood scale T/B) */
+    int32_t latent;                /* SVBASL_LATENT_* */
+    int32_t cov_llt;               /* 0: KL uses chol^T chol (svb); 1: chol chol^T */
+    int32_t prior_type[SVBASL_MAX_PAR];
+    float prior_mean[SVBASL_MAX_PAR];   /* internal-space prior moments, noise last */
+    float prior_var[SVBASL_MAX_PAR];
+    float ard_phi_max;             /* svb clips phi to [0, 1e6]; <= 0 disables the clip */
+    float latent_weight;
+    float grad_scale;              /* d(cost)/d(param) scale: 1/n_vox_global (svb minimises the MEAN cost) */
+    /* posterior state [n_state][ld]: mean[P'], logvar[P'], offdiag[P'(P'-1)/2] rows (1,0),(2,0),(2,1),..,
+     * then one log-phi row per ARD parameter */
+    float *state;
+    float *state_out;              /* where the updated state is written; NULL = in place.  Must differ from
+                                      `state` when a spatial prior reads neighbours' state (ping-pong) */
+    /* data / time points.  Row r of the batch is full-array row t_row0 + r*t_row_stride (svb's strided
+     * time-point mini-batches).  tpts may be NULL: then t = ti[row] + zoff[w] (aslrest.py:438-440) */
+    const float *data;             /* [T][ld] */
+    const float *tpts;             /* [T][ld] or NULL */
+    const float *ti;               /* [T] (device) when tpts == NULL */
+    const float *zoff;             /* [ld] slice offset z*slicedt, or NULL (= 0) */
+    int32_t t_row0, t_row_stride;
+    /* random draws: eps [P'][S][ld] read from memory when non-NULL (parity mode, the reference's
+     * tf.random_normal is not reproducible); otherwise Philox4x32-10 keyed on (seed, step, global voxel) */
+    const float *eps;
+    uint64_t seed;
+    /* spatial prior ("M"): neighbour table [6][ld] of LOCAL voxel indices, -1 = none.  The local arrays
+     * cover a contiguous global range [lower halo | owned | upper halo]; halo voxels are only read */
+    const int32_t *neighbours;
+    const float *log_ak;           /* [n spatial params] device */
+    double *ak_grad;               /* [n spatial params] device accumulators: d(sum cost)/d(log ak) */
+} svbasl_engine;
+
+/* TensorFlow-form Adam (tf.train.AdamOptimizer): m,v [n_state][ld]; lr_t[step] precomputed on the
+ * host: lr*sqrt(1-b2^t)/(1-b1^t), t = step+1 */
+typedef struct svbasl_adam {
+    float *m, *v;
+    const float *lr_t;             /* device [>= step0 + n_iters] */
+    float beta1, beta2, epsilon;
+    int64_t step0;                 /* global index of the first iteration of this launch */
+    int32_t n_iters;               /* iterations fused into this launch (>1 only without spatial priors) */
+    int32_t n_batches;             /* time-point mini-batches per epoch: row0 = (step % n_batches) */
+} svbasl_adam;
+
+const char *svbasl_last_error(void);
+int svbasl_abi_version(void);
+/* number of model parameters P for a model descriptor (len(model.params), aslrest.py:183-246) or <0 */
+int svbasl_model_n_params(const svbasl_model *model);
+/* rows of the state array for (model, engine priors) or <0 */
+int svbasl_n_state(const svbasl_model *model, const svbasl_engine *engine);
+
+/* Model.evaluate / ievaluate (aslrest.py:248-340, aslrest_disp.py:48-67, aslnn.py:93-126).
+ * params [P][n_rows] (row = voxel*S + sample, as the reference's [P,W,S,1]),
+ * tpts [n_t_rows][B] row-major with n_t_rows == n_rows/rows_per_t (W or 1: the reference's [W,1,B] / [1,1,B]),
+ * out [n_rows][B] row-major (the reference's [W,S,B]).  pv arrays in `model` are indexed by voxel = row / S. */
+int svbasl_evaluate(const svbasl_model *model, const float *params, const float *tpts, float *out,
+                    int64_t n_rows, int32_t n_samples, int32_t n_batch, int64_t n_t_rows, void *stream);
+
+/* One evaluation of the per-voxel cost (negative free energy) and its gradient with respect to the
+ * posterior state - the body of svb's sess.run(cost/gradients) for this plugin family.
+ * cost [ld] per-voxel cost (may be NULL); grad [n_state][ld] = grad_scale * d(sum cost)/d(state);
+ * cost_sum device double[1] accumulates sum of per-voxel cost (may be NULL). */
+int svbasl_elbo_grad(const svbasl_model *model, const svbasl_engine *engine, int64_t step,
+                     float *cost, float *grad, double *cost_sum, void *stream);
+
+/* Fused iteration(s): ELBO + gradient + Adam update of the posterior state in place - the body of
+ * svb's sess.run(optimize).  cost_sum device double[adam->n_iters] (one per fused iteration, may be NULL);
+ * nan_count device int64[1] counts voxels whose update was skipped for non-finite gradients (may be NULL). */
+int svbasl_step(const svbasl_model *model, const svbasl_engine *engine, const svbasl_adam *adam,
+                double *cost_sum, long long *nan_count, void *stream);
+
+/* Adam update of the global spatial-precision hyper-parameters from ak_grad (after any allreduce). */
+int svbasl_hyper_step(float *log_ak, float *m, float *v, const double *ak_grad, int32_t n, float grad_scale,
+                      float lr_t, float beta1, float beta2, float epsilon, void *stream);
+
+/* Write the Philox stream the fused kernels consume: eps [P'][S][ld] for `step`. */
+int svbasl_fill_eps(float *eps, int64_t n_vox, int64_t ld, int64_t vox_offset, int32_t n_par, int32_t n_samples,
+                    uint64_t seed, int64_t step, void *stream);
+
+/* Posterior initialisers on device (aslrest.py:461-520, svb noise init): data [T][ld] ->
+ * mean_t (>=floor), max_t (>=floor), variance_t (>=1) per voxel, time of max. Any output may be NULL. */
+int svbasl_init_stats(const float *data, const float *tpts, int64_t n_vox, int64_t ld, int32_t t_full,
+                      float *mean_t, float *max_t, float *var_t, float *t_at_max, void *stream);
+
+/* Model fit (mean prediction at posterior mean) for save_model_fit: out [T][ld]. */
+int svbasl_model_fit(const svbasl_model *model, const svbasl_engine *engine, float *out, void *stream);
+
+/* End-to-end iteration with HOST buffers, as svb feeds each batch through feed_dict: copies the
+ * batch rows of data/tpts from pinned host memory, runs svbasl_step, copies the mean cost back.
+ * Double-buffered on two internal streams; call svbasl_host_sync() before reading costs. */
+typedef struct svbasl_host_ctx svbasl_host_ctx;
+int svbasl_host_ctx_create(svbasl_host_ctx **ctx, int64_t ld, int32_t n_batch);
+int svbasl_host_ctx_destroy(svbasl_host_ctx *ctx);
+int svbasl_step_host(svbasl_host_ctx *ctx, const svbasl_model *model, const svbasl_engine *engine,
+                     const svbasl_adam *adam, const float *host_data /*[B][ld]*/, const float *host_tpts /*[B][ld]*/,
+                     double *host_cost_sum /* pinned, [1] */);
+int svbasl_host_sync(svbasl_host_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVBASL_H */

@@ -1,0 +1,380 @@
+// capi.cu - the extern "C" surface declared in include/svbasl.h: argument validation, dispatch on the
+// model layout to the matching kernel instantiation, and the small stand-alone kernels (RNG fill,
+// initialisation statistics, hyper-parameter Adam, host-staged iteration).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "kernels.cuh"
+#include "_gen/groups.h"
+
+namespace svb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static uint32_t canonical_flags(const svbasl_model *m) {
+    uint32_t f = m->flags;
+    if (m->kind == SVBASL_MODEL_ASLREST) {
+        f &= (SVBASL_F_CASL | SVBASL_F_INFERATT | SVBASL_F_INFERART | SVBASL_F_INCWM | SVBASL_F_INFERWM |
+              SVBASL_F_INFERT1 | SVBASL_F_ARTONLY);
+        if (f & SVBASL_F_ARTONLY) f |= SVBASL_F_INFERART;                      // aslrest.py:137-138
+        if (f & SVBASL_F_INFERWM) f |= SVBASL_F_INCWM;                        // aslrest.py:103-105
+        if (f & SVBASL_F_ARTONLY) f &= ~(uint32_t)(SVBASL_F_INCWM | SVBASL_F_INFERWM);
+    }
+    return f;
+}
+
+static const KernelEntry *find_entry(const svbasl_model *m, int nbt, uint32_t mrfmask, bool want_eval) {
+    const uint32_t f = canonical_flags(m);
+    const KernelEntry *fallback = nullptr;
+    for (int g = 0; g < kNumEntryGroups; ++g) {
+        for (const KernelEntry *e = kEntryGroups[g](); e->kind >= 0; ++e) {
+            if (e->kind != m->kind || e->flags != f) continue;
+            if (want_eval) {
+                if (e->eval) return e;
+                continue;
+            }
+            if (e->mrfmask != mrfmask) continue;
+            if (e->nbt == nbt) return e;
+            if (e->nbt == 0) fallback = e;
+        }
+    }
+    return fallback;
+}
+
+static uint32_t mrf_mask(const svbasl_engine *e) {
+    uint32_t mask = 0;
+    for (int i = 0; i < e->n_par && i < SVBASL_MAX_PAR; ++i)
+        if (e->prior_type[i] == SVBASL_PRIOR_MRF) mask |= 1u << i;
+    return mask;
+}
+
+static int validate(const svbasl_model *m, const svbasl_engine *e, const KernelEntry **entry) {
+    if (!m || !e) { set_error("null descriptor"); return SVBASL_E_INVALID; }
+    if (e->n_vox < 0 || e->w_begin < 0 || e->ld < e->w_begin + e->n_vox) {
+        set_error("bad extents: n_vox=%lld w_begin=%lld ld=%lld", (long long)e->n_vox, (long long)e->w_begin, (long long)e->ld);
+        return SVBASL_E_INVALID;
+    }
+    if (e->n_samples < 1 || e->n_batch < 1 || e->t_full < 1 || e->t_row_stride < 1) {
+        set_error("bad sizes: S=%d B=%d T=%d row_stride=%d", e->n_samples, e->n_batch, e->t_full, e->t_row_stride);
+        return SVBASL_E_INVALID;
+    }
+    if (!e->state || !e->data || (!e->tpts && !e->ti)) { set_error("state, data and tpts|ti are required"); return SVBASL_E_INVALID; }
+    const uint32_t mask = mrf_mask(e);
+    if (mask && e->latent != SVBASL_LATENT_NUMERIC) {
+        set_error("spatial (M) priors need the sample-based latent loss");
+        return SVBASL_E_INVALID;
+    }
+    if (mask && (!e->neighbours || !e->log_ak)) { set_error("spatial prior without neighbours/log_ak"); return SVBASL_E_INVALID; }
+    const KernelEntry *k = find_entry(m, e->n_batch, mask, false);
+    if (!k) {
+        set_error("no kernel compiled for model kind=%d flags=0x%x spatial-mask=0x%x", m->kind, canonical_flags(m), mask);
+        return SVBASL_E_UNSUPPORTED;
+    }
+    if (e->n_par != k->n_params + 1) {
+        set_error("engine n_par=%d but the model has %d parameters (+1 noise)", e->n_par, k->n_params);
+        return SVBASL_E_INVALID;
+    }
+    if (m->kind == SVBASL_MODEL_ASLREST && (canonical_flags(m) & SVBASL_F_INFERT1) == 0 && !(m->t1 > 0.0f)) {
+        set_error("t1 must be positive");
+        return SVBASL_E_INVALID;
+    }
+    *entry = k;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void fill_eps_kernel(float *eps, int64_t n_vox, int64_t ld, int64_t vox_offset, int n_par, int n_samples,
+                                uint64_t seed, int64_t step) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_vox) return;
+    const int groups = (n_samples + 3) / 4;
+    for (int j = 0; j < n_par; ++j) {
+        for (int sg = 0; sg < groups; ++sg) {
+            float n4[4];
+            normal4(seed, step, vox_offset + w, j, sg, n4);
+            for (int k = 0; k < 4; ++k) {
+                const int s = 4 * sg + k;
+                if (s < n_samples) eps[((int64_t)j * n_samples + s) * ld + w] = n4[k];
+            }
+        }
+    }
+}
+
+__global__ void init_stats_kernel(const float *data, const float *tpts, int64_t n_vox, int64_t ld, int t_full,
+                                  float *mean_t, float *max_t, float *var_t, float *t_at_max) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_vox) return;
+    float sum = 0.0f, mx = -INFINITY, tmx = 0.0f;
+    for (int r = 0; r < t_full; ++r) {
+        const float y = data[(int64_t)r * ld + w];
+        sum += y;
+        if (y > mx) { mx = y; tmx = tpts ? tpts[(int64_t)r * ld + w] : 0.0f; }   // first maximum (tf.argmax)
+    }
+    const float mean = sum / (float)t_full;
+    float ss = 0.0f;
+    for (int r = 0; r < t_full; ++r) {
+        const float d = data[(int64_t)r * ld + w] - mean;
+        ss += d * d;
+    }
+    if (mean_t) mean_t[w] = mean;
+    if (max_t) max_t[w] = mx;
+    if (var_t) var_t[w] = ss / (float)t_full;                  // tf.nn.moments: population variance
+    if (t_at_max) t_at_max[w] = tmx;
+}
+
+__global__ void hyper_step_kernel(float *log_ak, float *m, float *v, const double *ak_grad, int n, float grad_scale,
+                                  float lr_t, float b1, float b2, float eps) {
+    const int k = threadIdx.x;
+    if (k >= n) return;
+    const float g = (float)(ak_grad[k] * (double)grad_scale);
+    const float mm = b1 * m[k] + (1.0f - b1) * g;
+    const float vv = b2 * v[k] + (1.0f - b2) * g * g;
+    m[k] = mm;
+    v[k] = vv;
+    log_ak[k] -= lr_t * mm / (sqrtf(vv) + eps);
+}
+
+}  // namespace svb
+
+using namespace svb;
+
+struct svbasl_host_ctx {
+    cudaStream_t copy_stream, run_stream;
+    cudaEvent_t copied[2], consumed[2], done;
+    float *d_data[2], *d_tpts[2];
+    double *d_cost;
+    int64_t ld;
+    int32_t n_batch;
+    int slot;
+    long long calls;
+};
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            set_error("%s: %s", #expr, cudaGetErrorString(_e));                             \
+            return SVBASL_E_CUDA;                                                           \
+        }                                                                                   \
+    } while (0)
+
+extern "C" {
+
+const char *svbasl_last_error(void) { return g_err; }
+
+int svbasl_abi_version(void) { return SVBASL_ABI_VERSION; }
+
+int svbasl_model_n_params(const svbasl_model *model) {
+    if (!model) { set_error("null model"); return SVBASL_E_INVALID; }
+    const KernelEntry *k = find_entry(model, 0, 0, true);
+    if (!k) {
+        set_error("no kernel compiled for model kind=%d flags=0x%x", model->kind, canonical_flags(model));
+        return SVBASL_E_UNSUPPORTED;
+    }
+    return k->n_params;
+}
+
+int svbasl_n_state(const svbasl_model *model, const svbasl_engine *engine) {
+    int p = svbasl_model_n_params(model);
+    if (p < 0) return p;
+    if (!engine) { set_error("null engine"); return SVBASL_E_INVALID; }
+    const int n = p + 1;
+    int n_ard = 0;
+    for (int i = 0; i < n; ++i) n_ard += (engine->prior_type[i] == SVBASL_PRIOR_ARD);
+    return 2 * n + n * (n - 1) / 2 + n_ard;
+}
+
+int svbasl_evaluate(const svbasl_model *model, const float *params, const float *tpts, float *out, int64_t n_rows,
+                    int32_t n_samples, int32_t n_batch, int64_t n_t_rows, void *stream) {
+    if (!model || !tpts || !out) { set_error("null argument"); return SVBASL_E_INVALID; }
+    const KernelEntry *k = find_entry(model, 0, 0, true);
+    if (!k) {
+        set_error("no kernel compiled for model kind=%d flags=0x%x", model->kind, canonical_flags(model));
+        return SVBASL_E_UNSUPPORTED;
+    }
+    if (k->n_params > 0 && !params) { set_error("null params"); return SVBASL_E_INVALID; }
+    if (n_rows < 0 || n_samples < 1 || n_batch < 1 || n_t_rows < 1 || (n_rows % n_t_rows) != 0 || (n_rows % n_samples) != 0) {
+        set_error("bad shapes: rows=%lld S=%d B=%d t_rows=%lld", (long long)n_rows, n_samples, n_batch, (long long)n_t_rows);
+        return SVBASL_E_INVALID;
+    }
+    EvalArgs a;
+    a.md = *model;
+    a.params = params;
+    a.tpts = tpts;
+    a.out = out;
+    a.n_rows = n_rows;
+    a.n_t_rows = n_t_rows;
+    a.n_samples = n_samples;
+    a.n_batch = n_batch;
+    return k->eval(a, (cudaStream_t)stream);
+}
+
+static int run_step(const svbasl_model *model, const svbasl_engine *engine, const svbasl_adam *adam, int64_t step,
+                    float *cost, float *grad, double *cost_sum, long long *nan_count, void *stream) {
+    const KernelEntry *k = nullptr;
+    int rc = validate(model, engine, &k);
+    if (rc) return rc;
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.md = *model;
+    a.e = *engine;
+    a.update = adam ? 1 : 0;
+    if (adam) {
+        if (!adam->m || !adam->v || !adam->lr_t || adam->n_iters < 1 || adam->n_batches < 1) {
+            set_error("bad adam descriptor");
+            return SVBASL_E_INVALID;
+        }
+        if (mrf_mask(engine) && (adam->n_iters != 1 || !engine->state_out || engine->state_out == engine->state)) {
+            set_error("spatial priors need n_iters == 1 and a separate state_out (neighbours read the old state)");
+            return SVBASL_E_INVALID;
+        }
+        a.ad = *adam;
+        step = adam->step0;
+    }
+    a.step = step;
+    a.cost = cost;
+    a.grad = grad;
+    a.cost_sum = cost_sum;
+    a.nan_count = nan_count;
+    return k->step(a, (cudaStream_t)stream);
+}
+
+int svbasl_elbo_grad(const svbasl_model *model, const svbasl_engine *engine, int64_t step, float *cost, float *grad,
+                     double *cost_sum, void *stream) {
+    return run_step(model, engine, nullptr, step, cost, grad, cost_sum, nullptr, stream);
+}
+
+int svbasl_step(const svbasl_model *model, const svbasl_engine *engine, const svbasl_adam *adam, double *cost_sum,
+                long long *nan_count, void *stream) {
+    if (!adam) { set_error("null adam descriptor"); return SVBASL_E_INVALID; }
+    return run_step(model, engine, adam, 0, nullptr, nullptr, cost_sum, nan_count, stream);
+}
+
+int svbasl_hyper_step(float *log_ak, float *m, float *v, const double *ak_grad, int32_t n, float grad_scale, float lr_t,
+                      float beta1, float beta2, float epsilon, void *stream) {
+    if (!log_ak || !m || !v || !ak_grad || n < 1 || n > SVBASL_MAX_SPATIAL) { set_error("bad hyper_step arguments"); return SVBASL_E_INVALID; }
+    hyper_step_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(log_ak, m, v, ak_grad, n, grad_scale, lr_t, beta1, beta2, epsilon);
+    return check_launch("hyper_step_kernel");
+}
+
+int svbasl_fill_eps(float *eps, int64_t n_vox, int64_t ld, int64_t vox_offset, int32_t n_par, int32_t n_samples,
+                    uint64_t seed, int64_t step, void *stream) {
+    if (!eps || n_vox < 0 || ld < n_vox || n_par < 1 || n_samples < 1) { set_error("bad fill_eps arguments"); return SVBASL_E_INVALID; }
+    if (n_vox == 0) return 0;
+    fill_eps_kernel<<<(unsigned)((n_vox + 127) / 128), 128, 0, (cudaStream_t)stream>>>(eps, n_vox, ld, vox_offset, n_par,
+                                                                                      n_samples, seed, step);
+    return check_launch("fill_eps_kernel");
+}
+
+int svbasl_init_stats(const float *data, const float *tpts, int64_t n_vox, int64_t ld, int32_t t_full, float *mean_t,
+                      float *max_t, float *var_t, float *t_at_max, void *stream) {
+    if (!data || n_vox < 0 || ld < n_vox || t_full < 1) { set_error("bad init_stats arguments"); return SVBASL_E_INVALID; }
+    if (n_vox == 0) return 0;
+    init_stats_kernel<<<(unsigned)((n_vox + 127) / 128), 128, 0, (cudaStream_t)stream>>>(data, tpts, n_vox, ld, t_full, mean_t,
+                                                                                        max_t, var_t, t_at_max);
+    return check_launch("init_stats_kernel");
+}
+
+int svbasl_model_fit(const svbasl_model *model, const svbasl_engine *engine, float *out, void *stream) {
+    if (!model || !engine || !out) { set_error("null argument"); return SVBASL_E_INVALID; }
+    const KernelEntry *k = find_entry(model, 0, 0, true);
+    if (!k) { set_error("no kernel compiled for model kind=%d flags=0x%x", model->kind, canonical_flags(model)); return SVBASL_E_UNSUPPORTED; }
+    if (engine->n_par != k->n_params + 1 || !engine->state || (!engine->tpts && !engine->ti)) {
+        set_error("bad engine descriptor for model_fit");
+        return SVBASL_E_INVALID;
+    }
+    FitArgs a;
+    a.md = *model;
+    a.e = *engine;
+    a.out = out;
+    return k->fit(a, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-staged iteration: the reference feeds every batch from host memory (sess.run(feed_dict)); here
+// the batch of iteration i+1 is copied on a second stream while iteration i computes.
+int svbasl_host_ctx_create(svbasl_host_ctx **out, int64_t ld, int32_t n_batch) {
+    if (!out || ld < 1 || n_batch < 1) { set_error("bad host_ctx arguments"); return SVBASL_E_INVALID; }
+    svbasl_host_ctx *c = new svbasl_host_ctx();
+    memset(c, 0, sizeof(*c));
+    c->ld = ld;
+    c->n_batch = n_batch;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->run_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&c->copied[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->consumed[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaMalloc(&c->d_data[i], sizeof(float) * ld * n_batch));
+        CUDA_TRY(cudaMalloc(&c->d_tpts[i], sizeof(float) * ld * n_batch));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc(&c->d_cost, sizeof(double) * 2));
+    *out = c;
+    return 0;
+}
+
+int svbasl_host_ctx_destroy(svbasl_host_ctx *c) {
+    if (!c) return 0;
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamSynchronize(c->run_stream);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->d_data[i]);
+        cudaFree(c->d_tpts[i]);
+        cudaEventDestroy(c->copied[i]);
+        cudaEventDestroy(c->consumed[i]);
+    }
+    cudaFree(c->d_cost);
+    cudaEventDestroy(c->done);
+    cudaStreamDestroy(c->copy_stream);
+    cudaStreamDestroy(c->run_stream);
+    delete c;
+    return 0;
+}
+
+int svbasl_step_host(svbasl_host_ctx *c, const svbasl_model *model, const svbasl_engine *engine, const svbasl_adam *adam,
+                     const float *host_data, const float *host_tpts, double *host_cost_sum) {
+    if (!c || !engine || !adam || !host_data || !host_tpts) { set_error("null argument"); return SVBASL_E_INVALID; }
+    if (engine->ld != c->ld || engine->n_batch != c->n_batch) { set_error("engine does not match the host context"); return SVBASL_E_INVALID; }
+    const int s = c->slot;
+    const size_t bytes = sizeof(float) * (size_t)c->ld * (size_t)c->n_batch;
+    // the staging slot may only be overwritten once the iteration that used it two calls ago has finished
+    if (c->calls >= 2) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->consumed[s], 0));
+    CUDA_TRY(cudaMemcpyAsync(c->d_data[s], host_data, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_tpts[s], host_tpts, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaEventRecord(c->copied[s], c->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->run_stream, c->copied[s], 0));
+    svbasl_engine e = *engine;
+    e.data = c->d_data[s];
+    e.tpts = c->d_tpts[s];
+    e.t_row0 = 0;
+    e.t_row_stride = 1;
+    svbasl_adam ad = *adam;
+    ad.n_iters = 1;
+    ad.n_batches = 1;
+    double *d_cost = host_cost_sum ? c->d_cost + s : nullptr;
+    if (d_cost) CUDA_TRY(cudaMemsetAsync(d_cost, 0, sizeof(double), c->run_stream));
+    int rc = svbasl_step(model, &e, &ad, d_cost, nullptr, c->run_stream);
+    if (rc) return rc;
+    if (d_cost) CUDA_TRY(cudaMemcpyAsync(host_cost_sum, d_cost, sizeof(double), cudaMemcpyDeviceToHost, c->run_stream));
+    CUDA_TRY(cudaEventRecord(c->consumed[s], c->run_stream));
+    c->slot ^= 1;
+    c->calls++;
+    return 0;
+}
+
+int svbasl_host_sync(svbasl_host_ctx *c) {
+    if (!c) { set_error("null context"); return SVBASL_E_INVALID; }
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(c->run_stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,54 @@
+// compat.h - lets the per-voxel device code (models + fused ELBO/grad/Adam body) also be compiled by
+// a plain host compiler.  The host build exists ONLY for tests/hostsim (CPU checks of the kernel
+// arithmetic against the oracle in the GPU-less build container); libsvbasl.so never contains it.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define SVB_HD __host__ __device__ __forceinline__
+#define SVB_D __device__ __forceinline__
+#else
+#define SVB_HD inline
+#define SVB_D inline
+#endif
+
+namespace svb {
+
+#if defined(__CUDA_ARCH__)
+SVB_D float fexp(float x) { return __expf(x); }            // FMUL + MUFU.EX2
+SVB_D float fexp2(float x) { return exp2f(x); }
+SVB_D float flog(float x) { return __logf(x); }            // MUFU.LG2 + FMUL
+SVB_D float frcp(float x) { return __frcp_rn(x); }
+SVB_D float fdiv(float a, float b) { return __fdividef(a, b); }
+SVB_D float fsqrt(float x) { return __fsqrt_rn(x); }
+SVB_D void fsincos2pi(float u, float *s, float *c) { __sincosf(6.283185307179586f * u, s, c); }
+SVB_D uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+SVB_D float ferf(float x) { return erff(x); }
+SVB_D float ftanh(float x) {                               // 1 - 2/(exp(2x)+1): ~2 ulp, MUFU.EX2 + MUFU.RCP
+    float e = __expf(2.0f * x);
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+SVB_D bool finite_f(float x) { return isfinite(x); }
+#else
+SVB_HD float fexp(float x) { return expf(x); }
+SVB_HD float fexp2(float x) { return exp2f(x); }
+SVB_HD float flog(float x) { return logf(x); }
+SVB_HD float frcp(float x) { return 1.0f / x; }
+SVB_HD float fdiv(float a, float b) { return a / b; }
+SVB_HD float fsqrt(float x) { return sqrtf(x); }
+SVB_HD void fsincos2pi(float u, float *s, float *c) {
+    float a = 6.283185307179586f * u;
+    *s = sinf(a);
+    *c = cosf(a);
+}
+SVB_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+SVB_HD float ferf(float x) { return erff(x); }
+SVB_HD float ftanh(float x) { return tanhf(x); }
+SVB_HD bool finite_f(float x) { return isfinite(x); }
+#endif
+
+SVB_HD float fmin2(float a, float b) { return a < b ? a : b; }
+SVB_HD float fmax2(float a, float b) { return a > b ? a : b; }
+
+}  // namespace svb

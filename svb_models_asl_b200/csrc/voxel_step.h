@@ -1,0 +1,427 @@
+// voxel_step.h - one voxel's share of an SVB iteration, entirely in registers:
+//   reparameterised samples theta_s = mu + L eps_s from the per-voxel MVN posterior,
+//   model prediction + analytic model derivatives per (sample, time point),
+//   Gaussian-noise negative log-likelihood, latent loss (sample-based or closed-form KL) against
+//   N / ARD / spatial-MRF priors, the hand-derived gradient with respect to (mu, log-variance,
+//   Cholesky off-diagonals, ARD log-precision), and optionally the TensorFlow-form Adam update.
+//
+// This is the part of the external svb engine (SvbFit graph: posterior.sample -> model.evaluate ->
+// noise.log_likelihood -> latent loss -> tf.gradients -> AdamOptimizer)
+// that sits on the hot path around /root/reference/svb_models_asl/aslrest.py:248-340.  Backward-pass algebra:
+// SURVEY.md Appendix A.3 / DESIGN.md section 3.  One thread owns one voxel; nothing of size [W,S,B] ever exists.
+#pragma once
+#include "compat.h"
+#include "philox.h"
+#include "../../include/svbasl.h"
+
+namespace svb {
+
+SVB_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }       // lower triangle incl. diagonal
+SVB_HD constexpr int stri(int i, int j) { return i * (i - 1) / 2 + j; }      // strict lower triangle (state order)
+
+// Residual accumulator handed to Model::run(): keeps the batch's data/time points in registers (NBT > 0)
+// or re-reads them through L1 (NBT == 0, any batch size).
+template <int P, int NBT>
+struct BatchAcc {
+    static constexpr int NB = NBT;
+    float y[NBT > 0 ? NBT : 1], t[NBT > 0 ? NBT : 1];
+    const float *yp, *tp, *tip;     // dynamic mode: voxel-column bases
+    int64_t stride;                 // floats between consecutive batch rows
+    int ti_stride;
+    float zoff;
+    int nb;
+    float ssd;
+    float G[P > 0 ? P : 1];
+
+    SVB_HD void load(const svbasl_engine &e, int64_t w, int row0) {
+        nb = e.n_batch;
+        stride = (int64_t)e.t_row_stride * e.ld;
+        yp = e.data + (int64_t)row0 * e.ld + w;
+        tp = e.tpts ? e.tpts + (int64_t)row0 * e.ld + w : nullptr;
+        tip = e.ti ? e.ti + row0 : nullptr;
+        ti_stride = e.t_row_stride;
+        zoff = (e.zoff && !e.tpts) ? e.zoff[w] : 0.0f;
+        if (NBT > 0) {
+#pragma unroll
+            for (int b = 0; b < (NBT > 0 ? NBT : 1); ++b) {
+                y[b] = yp[b * stride];
+                t[b] = tp ? tp[b * stride] : tip[b * ti_stride] + zoff;
+            }
+        }
+    }
+    SVB_HD int n() const { return nb; }
+    SVB_HD float time(int b) const {
+        if (NBT > 0) return t[b];
+        return tp ? tp[b * stride] : tip[b * ti_stride] + zoff;
+    }
+    SVB_HD void reset() {
+        ssd = 0.0f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) G[p] = 0.0f;
+    }
+    SVB_HD void add(int b, float pred, const float *d) {
+        float r = pred - (NBT > 0 ? y[b] : yp[b * stride]);
+        ssd += r * r;
+#pragma unroll
+        for (int p = 0; p < P; ++p) G[p] += r * d[p];
+    }
+};
+
+SVB_HD constexpr int popc_below(uint32_t mask, int i) {     // set bits of mask strictly below bit i
+    int n = 0;
+    for (int j = 0; j < i; ++j) n += (mask >> j) & 1u;
+    return n;
+}
+
+// MRFMASK: compile-time set of parameters carrying the spatial ("M") prior (bit i = parameter i); the host
+// checks that engine.prior_type agrees.  Keeps the neighbours' samples in registers with static indices.
+template <class M, int NBT, uint32_t MRFMASK>
+struct VoxelStep {
+    static constexpr bool MRF = MRFMASK != 0;
+    static constexpr int NSP = MRF ? popc_below(MRFMASK, 32) : 1;
+    static constexpr bool is_mrf(int i) { return ((MRFMASK >> i) & 1u) != 0; }
+    static constexpr int sp_of(int i) { return popc_below(MRFMASK, i); }
+    static constexpr int P = M::P;
+    static constexpr int N = P + 1;                 // noise last
+    static constexpr int NL = N * (N - 1) / 2;
+    static constexpr int NT = N * (N + 1) / 2;
+
+    // posterior state of this voxel
+    float mu[N], lv[N], od[NL > 0 ? NL : 1];
+    float lphi[N];                                  // ARD log phi (only ARD slots used)
+    // gradients of grad_scale*cost (filled by elbo_grad)
+    float g_mu[N], g_lv[N], g_od[NL > 0 ? NL : 1], g_lphi[N];
+    int n_ard;
+
+    SVB_HD int ard_row(const svbasl_engine &e, int i) const {   // state row of parameter i's log phi
+        int k = 0;
+        for (int j = 0; j < i; ++j) k += (e.prior_type[j] == SVBASL_PRIOR_ARD);
+        return 2 * N + NL + k;
+    }
+
+    SVB_HD void load(const svbasl_engine &e, int64_t w) {
+        const float *s = e.state + w;
+        n_ard = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            mu[i] = s[(int64_t)i * e.ld];
+            lv[i] = s[(int64_t)(N + i) * e.ld];
+            lphi[i] = 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < NL; ++k) od[k] = s[(int64_t)(2 * N + k) * e.ld];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (e.prior_type[i] == SVBASL_PRIOR_ARD) {
+                lphi[i] = s[(int64_t)(2 * N + NL + n_ard) * e.ld];
+                ++n_ard;
+            }
+        }
+    }
+
+    // theta_p of neighbour voxel u for the 4 samples of group sg, recomputed from its state and its own
+    // draws (counter-based RNG keyed on the global voxel) or read from the eps array in parity mode.
+    static SVB_HD void neighbour_theta4(const svbasl_engine &e, int64_t step, int64_t u, int p, int sg, float th[4]) {
+        const float *st = e.state + u;
+        const float m = st[(int64_t)p * e.ld];
+        th[0] = th[1] = th[2] = th[3] = m;
+#pragma unroll 1
+        for (int j = 0; j <= p; ++j) {
+            const float l = (j == p) ? fexp(0.5f * st[(int64_t)(N + p) * e.ld])
+                                     : st[(int64_t)(2 * N + stri(p, j)) * e.ld];
+            float n4[4];
+            if (e.eps) {
+                for (int k = 0; k < 4; ++k) {
+                    int s = 4 * sg + k;
+                    n4[k] = s < e.n_samples ? e.eps[((int64_t)j * e.n_samples + s) * e.ld + u] : 0.0f;
+                }
+            } else {
+                normal4(e.seed, step, e.vox_offset + u, j, sg, n4);
+            }
+            for (int k = 0; k < 4; ++k) th[k] += l * n4[k];
+        }
+    }
+
+    // Cost of this voxel for one batch, gradients left in g_*.  Returns the un-scaled cost.
+    SVB_HD float elbo_grad(const svbasl_model &md, const svbasl_engine &e, int64_t w, int64_t step, int row0) {
+        const int S = e.n_samples;
+        const float Tf = (float)e.t_full;
+        const float scale = Tf / (float)e.n_batch;
+        const float lw = e.latent_weight;
+        const bool numeric = (e.latent == SVBASL_LATENT_NUMERIC);
+        typename M::Vox vox = M::load_vox(md, w);
+        BatchAcc<P, NBT> acc;
+        acc.load(e, w, row0);
+
+        float sd[N];
+        float pm[N], pinv[N], plog[N], phi_live[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            sd[i] = fexp(0.5f * lv[i]);
+            pm[i] = e.prior_mean[i];
+            if (e.prior_type[i] == SVBASL_PRIOR_ARD) {
+                float phi = fexp(lphi[i]);
+                bool clipped = (e.ard_phi_max > 0.0f) && (phi > e.ard_phi_max);
+                phi = clipped ? e.ard_phi_max : phi;
+                pinv[i] = phi;
+                plog[i] = -flog(phi);
+                phi_live[i] = clipped ? 0.0f : 1.0f;
+            } else {
+                pinv[i] = 1.0f / e.prior_var[i];
+                plog[i] = flog(e.prior_var[i]);
+                phi_live[i] = 0.0f;
+            }
+        }
+        float a_mu[N], a_L[NT], a_phi[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) { a_mu[i] = 0.0f; a_phi[i] = 0.0f; }
+#pragma unroll
+        for (int k = 0; k < NT; ++k) a_L[k] = 0.0f;
+        float cost = 0.0f;
+        float ak_part[SVBASL_MAX_SPATIAL] = {0.0f, 0.0f, 0.0f, 0.0f};
+
+        float eg[N][4];                               // draws of the current group of 4 samples
+        float nth[NSP][MRF ? 6 : 1][4];               // neighbours' samples of the same group
+        int nbr_idx[MRF ? 6 : 1];
+        if (MRF) {
+#pragma unroll
+            for (int nbr = 0; nbr < (MRF ? 6 : 1); ++nbr) nbr_idx[nbr] = e.neighbours[(int64_t)nbr * e.ld + w];
+        }
+        for (int s = 0; s < S; ++s) {
+            const int k4 = s & 3;
+            if (MRF && k4 == 0) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    if (is_mrf(i)) {
+#pragma unroll
+                        for (int nbr = 0; nbr < (MRF ? 6 : 1); ++nbr) {
+                            if (nbr_idx[nbr] >= 0)
+                                neighbour_theta4(e, step, nbr_idx[nbr], i, s >> 2, nth[MRF ? sp_of(i) : 0][nbr]);
+                        }
+                    }
+                }
+            }
+            float eps[N];
+            if (e.eps) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) eps[j] = e.eps[((int64_t)j * S + s) * e.ld + w];
+            } else {
+                if (k4 == 0) {
+#pragma unroll
+                    for (int j = 0; j < N; ++j) normal4(e.seed, step, e.vox_offset + w, j, s >> 2, eg[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < N; ++j)
+                    eps[j] = k4 == 0 ? eg[j][0] : (k4 == 1 ? eg[j][1] : (k4 == 2 ? eg[j][2] : eg[j][3]));
+            }
+            float th[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                float v = mu[i] + sd[i] * eps[i];
+#pragma unroll
+                for (int j = 0; j < i; ++j) v += od[stri(i, j)] * eps[j];
+                th[i] = v;
+            }
+            float x[P > 0 ? P : 1], dx[P > 0 ? P : 1];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int code = M::xf(p);
+                if (code == SVBASL_XF_EXP) { x[p] = fexp(th[p]); dx[p] = x[p]; }
+                else if (code == SVBASL_XF_ABS) { x[p] = fabsf(th[p]); dx[p] = th[p] < 0.0f ? -1.0f : 1.0f; }
+                else { x[p] = th[p]; dx[p] = 1.0f; }
+            }
+            acc.reset();
+            M::run(md, vox, x, acc);
+
+            const float thn = th[N - 1];
+            const float inv_nv = fexp(-thn);
+            const float c_ssd = scale * acc.ssd * inv_nv;
+            cost += 0.5f * (Tf * thn + c_ssd);
+            float g[N];
+#pragma unroll
+            for (int p = 0; p < P; ++p) g[p] = scale * inv_nv * acc.G[p] * dx[p];
+            g[N - 1] = 0.5f * (Tf - c_ssd);
+            if (numeric) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    if (MRF && is_mrf(i)) {
+                        // -E_s[ 1/2 log ak - ak/4 sum_u (x_w - x_u)^2 ]  
+                        const int sp = MRF ? sp_of(i) : 0;
+                        const float lak = e.log_ak[sp];
+                        const float ak = fexp(lak);
+                        float sdx = 0.0f, sdx2 = 0.0f;
+#pragma unroll
+                        for (int nbr = 0; nbr < (MRF ? 6 : 1); ++nbr) {
+                            if (nbr_idx[nbr] >= 0) {
+                                const float *q4 = nth[sp][nbr];
+                                float tu = k4 == 0 ? q4[0] : (k4 == 1 ? q4[1] : (k4 == 2 ? q4[2] : q4[3]));
+                                float dxu = th[i] - tu;
+                                sdx += dxu;
+                                sdx2 += dxu * dxu;
+                            }
+                        }
+                        cost += lw * (-0.5f * lak + 0.25f * ak * sdx2);
+                        g[i] += lw * ak * sdx;          // own term + the symmetric term of each neighbour's cost
+                        ak_part[sp] += lw * (-0.5f + 0.25f * ak * sdx2);
+                    } else {
+                        const float dth = th[i] - pm[i];
+                        const float zz = dth * pinv[i];
+                        g[i] += lw * zz;
+                        cost += lw * 0.5f * (plog[i] + dth * zz);
+                        a_phi[i] += lw * 0.5f * (dth * zz - 1.0f);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                a_mu[i] += g[i];
+#pragma unroll
+                for (int j = 0; j <= i; ++j) a_L[tri(i, j)] += g[i] * eps[j];
+            }
+        }
+        const float invS = 1.0f / (float)S;
+        cost *= invS;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { a_mu[i] *= invS; a_phi[i] *= invS; }
+#pragma unroll
+        for (int k = 0; k < NT; ++k) a_L[k] *= invS;
+        for (int k = 0; k < SVBASL_MAX_SPATIAL; ++k) ak_part[k] *= invS;
+
+        if (numeric) {
+            // entropy term -1/2 log det(cov) = -sum_i log L_ii
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                cost -= lw * 0.5f * lv[i];
+                a_L[tri(i, i)] -= lw * frcp(sd[i]);
+            }
+        } else {
+            // closed-form KL( N(mu, cov) || N(pm, diag(pv)) ), cov = L^T L (svb) or L L^T
+            float kl = 0.0f;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const float dm = mu[i] - pm[i];
+                float cii = 0.0f;     // cov_ii
+                if (e.cov_llt) {
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) {
+                        const float l = (j == i) ? sd[i] : od[stri(i, j)];
+                        cii += l * l;
+                        a_L[tri(i, j)] += lw * l * pinv[i];
+                    }
+                } else {
+#pragma unroll
+                    for (int r = i; r < N; ++r) {
+                        const float l = (r == i) ? sd[i] : od[stri(r, i)];
+                        cii += l * l;
+                        a_L[tri(r, i)] += lw * l * pinv[i];
+                    }
+                }
+                kl += cii * pinv[i] + dm * dm * pinv[i] - 1.0f + plog[i] - lv[i];
+                a_mu[i] += lw * dm * pinv[i];
+                a_L[tri(i, i)] -= lw * frcp(sd[i]);
+                a_phi[i] = lw * 0.5f * (pinv[i] * (cii + dm * dm) - 1.0f);
+            }
+            cost += lw * 0.5f * kl;
+        }
+        const float gs = e.grad_scale;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            g_mu[i] = gs * a_mu[i];
+            g_lv[i] = gs * a_L[tri(i, i)] * 0.5f * sd[i];
+            g_lphi[i] = gs * a_phi[i] * phi_live[i];
+#pragma unroll
+            for (int j = 0; j < i; ++j) g_od[stri(i, j)] = gs * a_L[tri(i, j)];
+        }
+        for (int k = 0; k < SVBASL_MAX_SPATIAL; ++k) ak_out[k] = ak_part[k];
+        return cost;
+    }
+
+    float ak_out[SVBASL_MAX_SPATIAL];   // this voxel's share of d(sum cost)/d(log ak_k)
+
+    SVB_HD bool grads_finite() const {
+        float acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc += g_mu[i] * 0.0f + g_lv[i] * 0.0f + g_lphi[i] * 0.0f;
+#pragma unroll
+        for (int k = 0; k < NL; ++k) acc += g_od[k] * 0.0f;
+        return acc == 0.0f;               // NaN/Inf * 0 = NaN
+    }
+
+    SVB_HD void store_grads(const svbasl_engine &e, float *grad, int64_t w) const {
+        float *g = grad + w;
+        int a = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            g[(int64_t)i * e.ld] = g_mu[i];
+            g[(int64_t)(N + i) * e.ld] = g_lv[i];
+        }
+#pragma unroll
+        for (int k = 0; k < NL; ++k) g[(int64_t)(2 * N + k) * e.ld] = g_od[k];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (e.prior_type[i] == SVBASL_PRIOR_ARD) g[(int64_t)(2 * N + NL + a++) * e.ld] = g_lphi[i];
+    }
+
+    static SVB_HD float adam1(const svbasl_adam &ad, float lr_t, float x, float g, float *m, float *v) {
+        float mm = ad.beta1 * (*m) + (1.0f - ad.beta1) * g;
+        float vv = ad.beta2 * (*v) + (1.0f - ad.beta2) * g * g;
+        *m = mm;
+        *v = vv;
+        return x - lr_t * mm / (fsqrt(vv) + ad.epsilon);
+    }
+
+    // tf.train.AdamOptimizer step on this voxel's rows; moments streamed through global memory.
+    // With write_state the new state is stored too (always, unless iterations are being fused).
+    SVB_HD void adam_update(const svbasl_engine &e, const svbasl_adam &ad, float lr_t, int64_t w, bool write_state) {
+        float *m = ad.m + w, *v = ad.v + w, *s = (e.state_out ? e.state_out : e.state) + w;
+        int a = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            int64_t o = (int64_t)i * e.ld;
+            float mm = m[o], vv = v[o];
+            mu[i] = adam1(ad, lr_t, mu[i], g_mu[i], &mm, &vv);
+            m[o] = mm; v[o] = vv;
+            if (write_state) s[o] = mu[i];
+            o = (int64_t)(N + i) * e.ld;
+            mm = m[o]; vv = v[o];
+            lv[i] = adam1(ad, lr_t, lv[i], g_lv[i], &mm, &vv);
+            m[o] = mm; v[o] = vv;
+            if (write_state) s[o] = lv[i];
+        }
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            int64_t o = (int64_t)(2 * N + k) * e.ld;
+            float mm = m[o], vv = v[o];
+            od[k] = adam1(ad, lr_t, od[k], g_od[k], &mm, &vv);
+            m[o] = mm; v[o] = vv;
+            if (write_state) s[o] = od[k];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (e.prior_type[i] == SVBASL_PRIOR_ARD) {
+                int64_t o = (int64_t)(2 * N + NL + a++) * e.ld;
+                float mm = m[o], vv = v[o];
+                lphi[i] = adam1(ad, lr_t, lphi[i], g_lphi[i], &mm, &vv);
+                m[o] = mm; v[o] = vv;
+                if (write_state) s[o] = lphi[i];
+            }
+        }
+    }
+
+    SVB_HD void store_state(const svbasl_engine &e, int64_t w) const {
+        float *s = (e.state_out ? e.state_out : e.state) + w;
+        int a = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            s[(int64_t)i * e.ld] = mu[i];
+            s[(int64_t)(N + i) * e.ld] = lv[i];
+        }
+#pragma unroll
+        for (int k = 0; k < NL; ++k) s[(int64_t)(2 * N + k) * e.ld] = od[k];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (e.prior_type[i] == SVBASL_PRIOR_ARD) s[(int64_t)(2 * N + NL + a++) * e.ld] = lphi[i];
+    }
+};
+
+}  // namespace svb

@@ -1,0 +1,106 @@
+// TEST INFRASTRUCTURE ONLY.  Compiles the *device* per-voxel code (svb_models_asl_b200/csrc/voxel_step.h,
+// model_*.h, philox.h) with the host compiler so that the kernel arithmetic can be checked against the
+// oracle in the GPU-less build container (pytest -m "not gpu").  Never linked into libsvbasl.so and never
+// imported by the product package; on the GPU box the parity tests go through the real C ABI instead.
+#include <cstdio>
+#include <cstring>
+
+#include "voxel_step.h"
+#include "model_aslrest.h"
+#include "model_list.h"
+
+using namespace svb;
+
+template <class M, int NBT, uint32_t MRFMASK>
+static int run_step(const svbasl_model *md, const svbasl_engine *e, const svbasl_adam *ad, int64_t step0, float *cost,
+                    float *grad, double *cost_sum, double *ak_grad) {
+    const int n_iters = ad ? ad->n_iters : 1;
+    for (int64_t local = 0; local < e->n_vox; ++local) {
+        const int64_t w = e->w_begin + local;
+        VoxelStep<M, NBT, MRFMASK> vs;
+        vs.load(*e, w);
+        for (int it = 0; it < n_iters; ++it) {
+            const int64_t step = (ad ? ad->step0 : step0) + it;
+            const int row0 = (ad && ad->n_batches > 1) ? (int)(step % ad->n_batches) : e->t_row0;
+            float c = vs.elbo_grad(*md, *e, w, step, row0);
+            if (cost) cost[w] = c;
+            if (grad) vs.store_grads(*e, grad, w);
+            if (ad) {
+                if (vs.grads_finite() && c == c) vs.adam_update(*e, *ad, ad->lr_t[step], w, it == n_iters - 1);
+                else { if (it == n_iters - 1) vs.store_state(*e, w); c = 0.0f; }
+            }
+            if (cost_sum) cost_sum[it] += c;
+            if (MRFMASK != 0 && ak_grad)
+                for (int k = 0; k < VoxelStep<M, NBT, MRFMASK>::NSP; ++k) ak_grad[k] += vs.ak_out[k];
+        }
+    }
+    return 0;
+}
+
+template <class M>
+static int run_eval(const svbasl_model *md, const float *params, const float *tpts, float *out, int64_t n_rows,
+                    int n_samples, int n_batch, int64_t n_t_rows) {
+    const int64_t rows_per_t = n_rows / n_t_rows;
+    for (int64_t row = 0; row < n_rows; ++row) {
+        float x[M::P > 0 ? M::P : 1];
+        for (int p = 0; p < M::P; ++p) x[p] = params[(int64_t)p * n_rows + row];
+        typename M::Vox vx = M::load_vox(*md, row / n_samples);
+        for (int b = 0; b < n_batch; ++b)
+            out[row * n_batch + b] = M::predict(*md, vx, x, tpts[(row / rows_per_t) * n_batch + b]);
+    }
+    return 0;
+}
+
+static uint32_t canon(uint32_t f) {
+    if (f & SVBASL_F_ARTONLY) f |= SVBASL_F_INFERART;
+    if (f & SVBASL_F_INFERWM) f |= SVBASL_F_INCWM;
+    if (f & SVBASL_F_ARTONLY) f &= ~(uint32_t)(SVBASL_F_INCWM | SVBASL_F_INFERWM);
+    return f;
+}
+
+extern "C" int hostsim_n_params(const svbasl_model *md) {
+    const uint32_t f = canon(md->flags);
+#define X(F) if (md->kind == SVBASL_MODEL_ASLREST && f == F) return AslRest<F>::P;
+    HOSTSIM_ASLREST_FLAGS
+#undef X
+    return -1;
+}
+
+extern "C" int hostsim_evaluate(const svbasl_model *md, const float *params, const float *tpts, float *out,
+                                int64_t n_rows, int n_samples, int n_batch, int64_t n_t_rows) {
+    const uint32_t f = canon(md->flags);
+#define X(F) if (md->kind == SVBASL_MODEL_ASLREST && f == F) return run_eval<AslRest<F>>(md, params, tpts, out, n_rows, n_samples, n_batch, n_t_rows);
+    HOSTSIM_ASLREST_FLAGS
+#undef X
+    return -2;
+}
+
+// nbt: 0 = dynamic batch loop, 6 = register-resident batch (only for the fast-path layouts)
+extern "C" int hostsim_step(const svbasl_model *md, const svbasl_engine *e, const svbasl_adam *ad, int64_t step,
+                            float *cost, float *grad, double *cost_sum, double *ak_grad, int nbt) {
+    const uint32_t f = canon(md->flags);
+    uint32_t mask = 0;
+    for (int i = 0; i < e->n_par; ++i) if (e->prior_type[i] == SVBASL_PRIOR_MRF) mask |= 1u << i;
+    if (mask == 0 && nbt == 0) {
+#define X(F) if (md->kind == SVBASL_MODEL_ASLREST && f == F) return run_step<AslRest<F>, 0, 0>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
+        HOSTSIM_ASLREST_FLAGS
+#undef X
+    }
+#define Y(F, NBT, MASK) if (md->kind == SVBASL_MODEL_ASLREST && f == F && nbt == NBT && mask == MASK) return run_step<AslRest<F>, NBT, MASK>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
+    HOSTSIM_FAST
+#undef Y
+    return -2;
+}
+
+extern "C" void hostsim_fill_eps(float *eps, int64_t n_vox, int64_t ld, int64_t vox_offset, int n_par, int n_samples,
+                                 uint64_t seed, int64_t step) {
+    const int groups = (n_samples + 3) / 4;
+    for (int64_t w = 0; w < n_vox; ++w)
+        for (int j = 0; j < n_par; ++j)
+            for (int sg = 0; sg < groups; ++sg) {
+                float n4[4];
+                normal4(seed, step, vox_offset + w, j, sg, n4);
+                for (int k = 0; k < 4; ++k)
+                    if (4 * sg + k < n_samples) eps[((int64_t)j * n_samples + 4 * sg + k) * ld + w] = n4[k];
+            }
+}

@@ -1,0 +1,316 @@
+"""
+Parity of the kernel arithmetic with the oracle.
+
+Every test runs twice: through libsvbasl.so on the GPU (marked `gpu`; the parity tests proper) and through
+the host build of the same device headers (`hostsim`; runs in the GPU-less container so a broken formula is
+caught before GPU time is spent).  Tolerances are BASELINE.json's: forward signals 1e-5 relative (to the
+peak |signal| of the case), cost and gradients 1e-4 relative in float32.
+"""
+import math
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import asl_models as om
+from oracle import svb_engine as eng
+from tests import helpers as H
+
+BACKENDS = [pytest.param("hostsim", id="hostsim"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+
+FWD_TOL = 1e-5       # BASELINE.json north_star: forward signals within 1e-5 relative
+GRAD_TOL = 1e-4      # ELBO and gradients within 1e-4 relative in fp32
+
+
+@pytest.fixture(scope="module", params=BACKENDS)
+def be(request):
+    return H.Backend(request.param)
+
+
+CASE_CFG = {
+    "casl_tiss": dict(casl=True),
+    "pasl_tiss": dict(casl=False),
+    "casl_tiss_art": dict(casl=True, inferart=True),
+    "pasl_tiss_art": dict(casl=False, inferart=True),
+    "casl_noatt": dict(casl=True, inferatt=False),
+    "casl_artonly": dict(casl=True, artonly=True),
+    "casl_t1": dict(casl=True, infert1=True),
+    "pasl_t1_art": dict(casl=False, infert1=True, inferart=True),
+    "casl_pvc": dict(casl=True, incwm=True, inferwm=True, inferart=True, pc=0.98),
+    "casl_pvc_t1": dict(casl=True, incwm=True, inferwm=True, infert1=True, pc=0.98),
+}
+
+
+def _golden_cfg(case, rec):
+    kw = dict(CASE_CFG[case])
+    for k in ("pvgm", "pvwm"):
+        if k in rec:
+            kw[k] = rec[k]
+    return om.AslConfig(tau=1.8, t1b=1.65, **kw)
+
+
+@pytest.mark.parametrize("case", sorted(CASE_CFG))
+def test_evaluate_matches_reference_goldens(be, golden, case):
+    """Model.evaluate (aslrest.py:248-340) on the golden inputs of the reference source."""
+    rec = golden("aslrest_eval")[case]
+    cfg = _golden_cfg(case, rec)
+    out = be.evaluate(cfg, rec["params"], rec["t"], rec["params"].shape[2])
+    ref = rec["out64"]
+    scale = np.abs(ref).max()
+    err = np.abs(out - ref)
+    # elements that sit on a mask boundary may flip between float32 and float64 evaluation of tau+delt;
+    # the reference's own float32 run (out32) tells which ones those are
+    edge = np.abs(rec["out32"].astype(np.float64) - ref) > 50 * FWD_TOL * scale
+    assert edge.mean() < 0.01
+    assert err[~edge].max() <= FWD_TOL * scale, (case, err[~edge].max() / scale)
+
+
+def test_evaluate_edges_and_quick_test(be, golden):
+    g = golden("aslrest_edges")
+    cfg = om.AslConfig(casl=True, inferart=True, tau=1.8, t1b=1.65)
+    e = g["edges"]
+    out = be.evaluate(cfg, e["params"], e["t"], 1)
+    assert np.isfinite(out).all()
+    scale = np.abs(e["out64"]).max()
+    bad = np.abs(out - e["out64"]) > FWD_TOL * scale
+    # t == delt / t == tau+delt / t == deltblood+tau/2 exactly: follow the float32 reference run there
+    assert (np.abs(out - e["out32"])[bad] <= FWD_TOL * scale).all()
+    q = g["quick_test"]
+    cfgq = om.AslConfig(casl=True, tau=1.8, t1b=1.6, t1=1.3)
+    outq = be.evaluate(cfgq, q["params"], q["t"], 1)
+    np.testing.assert_allclose(outq, q["out64"], rtol=FWD_TOL)
+
+
+def test_evaluate_broadcast_shapes(be):
+    """params [P,n,1] x tpts [n,B] (gen_test_data.py:42-47) and a shared [1,1,B] time axis."""
+    cfg = om.AslConfig(casl=True)
+    rng = np.random.default_rng(3)
+    n = 37
+    params = np.stack([rng.uniform(1, 20, (n, 1, 1)), rng.uniform(0.6, 2.5, (n, 1, 1))]).astype(np.float32)
+    t_shared = np.asarray(H.TIS, dtype=np.float32).reshape(1, 1, -1)
+    t_full = np.repeat(t_shared, n, axis=0)
+    a = be.evaluate(cfg, params, t_shared, 1)
+    b = be.evaluate(cfg, params, t_full, 1)
+    np.testing.assert_array_equal(a, b)
+    ref = om.evaluate(cfg, [torch.as_tensor(p, dtype=torch.float64) for p in params],
+                      torch.as_tensor(t_full, dtype=torch.float64)).numpy()
+    assert np.abs(a - ref).max() <= FWD_TOL * np.abs(ref).max()
+
+
+GRAD_CASES = {
+    "casl_tiss": (dict(casl=True), {}),
+    "casl_tiss_art": (dict(casl=True, inferart=True), {}),
+    "pasl_tiss_art": (dict(casl=False, inferart=True), {}),
+    "casl_art_noard": (dict(casl=True, inferart=True), dict(ard=False)),
+    "casl_noatt_art": (dict(casl=True, inferart=True, inferatt=False), {}),
+    "casl_artonly": (dict(casl=True, artonly=True), {}),
+    "casl_t1": (dict(casl=True, infert1=True), {}),
+    "pasl_t1": (dict(casl=False, infert1=True), {}),
+    "casl_pvc_art": (dict(casl=True, incwm=True, inferwm=True, inferart=True, pc=0.98, pvgm="rand", pvwm="rand"), {}),
+    "casl_pvc_t1": (dict(casl=True, incwm=True, inferwm=True, infert1=True, pc=0.98, pvgm="rand", pvwm="rand"), {}),
+    "casl_incwm_fixed": (dict(casl=True, incwm=True, fwm=4.0, pvgm=0.6, pvwm=0.3), {}),
+}
+
+
+def _make(case, W, rng, **spec_kw):
+    cfg_kw, extra = GRAD_CASES[case]
+    cfg_kw = dict(cfg_kw)
+    for k in ("pvgm", "pvwm"):
+        if cfg_kw.get(k) == "rand":
+            cfg_kw[k] = rng.uniform(0.1, 0.45, W).astype(np.float32)
+    cfg = om.AslConfig(tau=1.8, t1b=1.65, **cfg_kw)
+    spec = H.aslrest_spec(cfg, **{**extra, **spec_kw})
+    return cfg, spec
+
+
+def _check_grads(cost, grad, ocost, ograd, tol=GRAD_TOL):
+    assert np.isfinite(cost).all() and np.isfinite(grad).all()
+    np.testing.assert_allclose(cost, ocost, rtol=tol, atol=tol * np.abs(ocost).max())
+    # per state row (one posterior variable over all voxels): relative error of the gradient vector
+    live = np.abs(ograd).max(axis=1) > 0
+    num = np.linalg.norm(grad.astype(np.float64) - ograd, axis=1)[live]
+    den = np.linalg.norm(ograd, axis=1)[live]
+    assert (num / den).max() <= tol, (num / den)
+    # and no single voxel far out: the erf edge of the arterial curve has slope 1/leadscale = 100, which
+    # amplifies the float32 rounding of (t - deltblood) in isolated voxels
+    assert H.rel_err(grad, ograd)[live].max() <= 3 * tol, H.rel_err(grad, ograd).ravel()
+
+
+@pytest.mark.parametrize("latent", ["numeric", "analytic"])
+@pytest.mark.parametrize("case", sorted(GRAD_CASES))
+def test_elbo_grad_matches_oracle(be, case, latent):
+    """Per-voxel cost and gradient vs torch-autograd through the op-for-op oracle, same eps."""
+    rng = np.random.default_rng(zlib.crc32(case.encode()))
+    W = 96
+    cfg, spec = _make(case, W, rng, latent=latent)
+    prob = H.synth_problem(cfg, spec, W, rng)
+    eps = rng.normal(size=(spec.n_par, spec.n_samples, W)).astype(np.float32)
+    ocost, ograd, _gh, _ = H.oracle_cost_grad(spec, prob, eps)
+    m = be.model_desc(cfg)
+    e, _b = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], eps)
+    cost, grad, csum = be.elbo_grad(m, e, spec.n_state)
+    _check_grads(cost, grad, ocost, ograd)
+    assert csum == pytest.approx(float(ocost.sum()), rel=GRAD_TOL)
+
+
+@pytest.mark.parametrize("case", ["casl_tiss", "casl_tiss_art"])
+def test_register_resident_batch_path(be, case):
+    """The B=6 fast path (batch held in registers) against the oracle; on the GPU the dispatcher picks it."""
+    rng = np.random.default_rng(5)
+    W = 200
+    cfg, spec = _make(case, W, rng)
+    prob = H.synth_problem(cfg, spec, W, rng)
+    eps = rng.normal(size=(spec.n_par, spec.n_samples, W)).astype(np.float32)
+    ocost, ograd, _gh, _ = H.oracle_cost_grad(spec, prob, eps)
+    m = be.model_desc(cfg)
+    e, _b = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], eps)
+    cost, grad, _ = be.elbo_grad(m, e, spec.n_state, nbt=6)
+    _check_grads(cost, grad, ocost, ograd)
+
+
+def test_time_point_minibatch_and_lowrank_times(be):
+    """T=48 (6 PLD x 8 repeats), B=6 strided batch rows i, i+n_batches, ... with likelihood scale T/B
+    (asl_example.py:26-30); time points given as the table ti[row] + z*slicedt (aslrest.py:438-440)."""
+    rng = np.random.default_rng(8)
+    W = 64
+    cfg = om.AslConfig(casl=True, tau=1.8, t1b=1.65)
+    spec = H.aslrest_spec(cfg, t_full=48)
+    prob = H.synth_problem(cfg, spec, W, rng, repeats=8)
+    rows, n_batches = eng.batch_rows(48, 6, 3)
+    assert rows == [3, 11, 19, 27, 35, 43] and n_batches == 8
+    eps = rng.normal(size=(spec.n_par, spec.n_samples, W)).astype(np.float32)
+    ocost, ograd, _gh, _ = H.oracle_cost_grad(spec, prob, eps, rows=rows)
+    m = be.model_desc(cfg)
+    e, _b = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], eps, n_batch=6, t_row0=3, t_row_stride=8)
+    cost, grad, _ = be.elbo_grad(m, e, spec.n_state, nbt=6)
+    _check_grads(cost, grad, ocost, ograd)
+    # same thing with t = ti[row] + zoff[w]
+    ti = np.repeat(np.asarray(H.TIS), 8).astype(np.float32)
+    zoff = (prob["tpts"][0] - ti[0]).astype(np.float32)
+    e2, _b2 = be.engine_desc(spec, prob["state"], prob["data"], None, eps, n_batch=6, t_row0=3, t_row_stride=8, ti=ti,
+                             zoff=zoff)
+    cost2, grad2, _ = be.elbo_grad(m, e2, spec.n_state, nbt=6)
+    _check_grads(cost2, grad2, ocost, ograd)
+
+
+def test_cov_convention_switch(be):
+    rng = np.random.default_rng(9)
+    W = 50
+    cfg, spec = _make("casl_tiss_art", W, rng, latent="analytic", cov="LLt")
+    prob = H.synth_problem(cfg, spec, W, rng)
+    eps = rng.normal(size=(spec.n_par, spec.n_samples, W)).astype(np.float32)
+    ocost, ograd, _gh, _ = H.oracle_cost_grad(spec, prob, eps)
+    m = be.model_desc(cfg)
+    e, _b = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], eps)
+    cost, grad, _ = be.elbo_grad(m, e, spec.n_state)
+    _check_grads(cost, grad, ocost, ograd)
+
+
+def test_adam_steps_follow_oracle(be):
+    """Five fused iterations (ELBO + gradient + TF-form Adam) track the oracle's trajectory."""
+    rng = np.random.default_rng(10)
+    W = 80
+    cfg, spec = _make("casl_tiss_art", W, rng)
+    prob = H.synth_problem(cfg, spec, W, rng)
+    n_it = 5
+    eps_all = rng.normal(size=(n_it, spec.n_par, spec.n_samples, W)).astype(np.float32)
+    ost, _ = eng.fit(spec, torch.as_tensor(prob["state"]), torch.zeros(0, dtype=torch.float64),
+                     torch.as_tensor(prob["data"].astype(np.float64)), torch.as_tensor(prob["tpts"].astype(np.float64)),
+                     n_it, 6, 0.05, lambda it: torch.as_tensor(eps_all[it], dtype=torch.float64))
+    m = be.model_desc(cfg)
+    e, bufs = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], eps_all[0])
+    ad, _ab = be.adam_desc(spec.n_state, W, 0.05, n_it)
+    for it in range(n_it):
+        eb = be.put(eps_all[it])
+        e.eps = be.ptr(eb)
+        ad.step0 = it
+        csum, nanc = be.step(m, e, ad, nbt=6)
+        assert nanc == 0 and np.isfinite(csum).all()
+    st = be.get(bufs["state"])
+    # Adam normalises the step to ~lr, so compare the *movement* of every parameter
+    moved = ost.numpy() - prob["state"]
+    err = np.abs((st - prob["state"]) - moved).max(axis=1) / np.maximum(np.abs(moved).max(axis=1), 1e-12)
+    # (worst voxel; Adam's m/sqrt(v) amplifies float32 rounding where a gradient is close to zero)
+    assert err.max() < 1e-2 and np.median(err) < 2e-4, err
+
+
+def test_nonfinite_gradients_skip_the_update(be):
+    rng = np.random.default_rng(11)
+    W = 40
+    cfg, spec = _make("casl_tiss", W, rng)
+    prob = H.synth_problem(cfg, spec, W, rng)
+    prob["data"][:, 7] = np.nan
+    eps = rng.normal(size=(spec.n_par, spec.n_samples, W)).astype(np.float32)
+    m = be.model_desc(cfg)
+    e, bufs = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], eps)
+    ad, _ab = be.adam_desc(spec.n_state, W, 0.05, 1)
+    csum, nanc = be.step(m, e, ad)
+    st = be.get(bufs["state"])
+    if be.kind == "cuda":
+        assert nanc == 1
+    assert np.isfinite(csum).all() and np.isfinite(st).all()
+    np.testing.assert_array_equal(st[:, 7], prob["state"][:, 7].astype(np.float32))
+    assert (st[:, 8] != prob["state"][:, 8].astype(np.float32)).any()
+
+
+def _grid_neighbours(shape):
+    X, Y, Z = shape
+    coords = np.stack(np.meshgrid(np.arange(X), np.arange(Y), np.arange(Z), indexing="ij"), -1).reshape(-1, 3)
+    return coords, eng.neighbour_table(coords, shape)
+
+
+@pytest.mark.parametrize("mrf", [(0,), (0, 1)])
+def test_spatial_prior_matches_oracle(be, mrf):
+    """Sample-based MRF prior: neighbours' samples are rebuilt from their state + draws."""
+    rng = np.random.default_rng(12)
+    shape = (4, 5, 3)
+    coords, nb = _grid_neighbours(shape)
+    W = len(coords)
+    cfg = om.AslConfig(casl=True, tau=1.8, t1b=1.65)
+    spec = H.aslrest_spec(cfg, mrf=mrf)
+    prob = H.synth_problem(cfg, spec, W, rng)
+    eps = rng.normal(size=(spec.n_par, spec.n_samples, W)).astype(np.float32)
+    log_ak = np.asarray([-1.5, -0.5][:len(mrf)], dtype=np.float32)
+    ocost, ograd, ogh, _ = H.oracle_cost_grad(spec, prob, eps, hyper=log_ak.astype(np.float64), neighbours=nb,
+                                              grad_scale=1.0 / W)
+    m = be.model_desc(cfg)
+    e, bufs = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], eps, neighbours=nb.T.copy(),
+                             log_ak=log_ak)
+    cost, grad, _ = be.elbo_grad(m, e, spec.n_state, nbt=6)
+    _check_grads(cost, grad, ocost, ograd)
+    ak_grad = be.get(bufs["ak_grad"])[:len(mrf)] / W
+    np.testing.assert_allclose(ak_grad, ogh, rtol=GRAD_TOL)
+
+
+def test_rng_stream_is_sharding_invariant_and_normal(be):
+    """Draws depend on (seed, step, global voxel) only; moments are those of N(0,1)."""
+    P, S, W = 5, 10, 4096
+    a = be.fill_eps(P, S, W, seed=7, step=3)
+    b = be.fill_eps(P, S, W // 2, seed=7, step=3, vox_offset=W // 2)
+    np.testing.assert_array_equal(a[:, :, W // 2:], b)
+    c = be.fill_eps(P, S, W, seed=7, step=4)
+    assert np.abs(np.corrcoef(a.ravel(), c.ravel())[0, 1]) < 0.02
+    x = a.ravel()
+    assert abs(x.mean()) < 0.02 and abs(x.std() - 1) < 0.02
+    assert abs((x ** 3).mean()) < 0.05 and abs((x ** 4).mean() - 3) < 0.15
+    # independence across parameters / samples of one voxel
+    flat = a.reshape(P * S, W)
+    cc = np.corrcoef(flat)
+    assert np.abs(cc - np.eye(P * S)).max() < 0.08
+
+
+def test_in_kernel_rng_equals_memory_eps(be):
+    """eps == NULL (Philox in registers) gives the same result as feeding the filled stream from memory."""
+    rng = np.random.default_rng(13)
+    W = 128
+    cfg, spec = _make("casl_tiss_art", W, rng)
+    prob = H.synth_problem(cfg, spec, W, rng)
+    eps = be.fill_eps(spec.n_par, spec.n_samples, W, seed=99, step=17)
+    m = be.model_desc(cfg)
+    e1, _ = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], eps, seed=99)
+    e2, _ = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], None, seed=99)
+    c1, g1, _ = be.elbo_grad(m, e1, spec.n_state, step=17, nbt=6)
+    c2, g2, _ = be.elbo_grad(m, e2, spec.n_state, step=17, nbt=6)
+    np.testing.assert_allclose(c1, c2, rtol=1e-5)
+    assert H.rel_err(g2, g1).max() < 1e-4
