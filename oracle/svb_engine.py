@@ -124,11 +124,14 @@ def voxel_cost(spec, state, hyper, data, t, eps, neighbours=None):
     B = data.shape[0]
     e = eps.permute(2, 0, 1)                                        # [W,P',S]
     theta = mean.unsqueeze(-1) + chol @ e                           # [W,P',S]   (sample = mean + chol eps)
-    ext = [transform(spec.xf[p], theta[:, p, :]).unsqueeze(-1) for p in range(n - 1)]
-    pred = model_predict(spec, ext, t.T.unsqueeze(1))               # [W,S,B]
+    # materialise every operand at the full [W,S,B] shape, as TF's tile/broadcast kernels do (and because
+    # torch's CPU broadcasting of [W,S,1] x [W,1,B] operands is ~50x slower than dense element-wise ops)
+    full = (state.shape[1], S, B)
+    ext = [transform(spec.xf[p], theta[:, p, :]).unsqueeze(-1).expand(full).contiguous() for p in range(n - 1)]
+    pred = model_predict(spec, ext, t.T.unsqueeze(1).expand(full).contiguous())   # [W,S,B]
     log_nv = theta[:, n - 1, :]                                     # noise is LogNormal: var = exp(theta_n)
     nv = torch.exp(log_nv)
-    ssd = torch.square(data.T.unsqueeze(1) - pred).sum(-1)          # [W,S]
+    ssd = torch.square(data.T.unsqueeze(1).expand(full).contiguous() - pred).sum(-1)          # [W,S]
     scale = spec.t_full / B
     recon = (0.5 * (log_nv * spec.t_full + scale * ssd / nv)).mean(1)
 

@@ -1,0 +1,266 @@
+"""
+Device-side operators of the ASL SVB hot path, as thin Python objects over the C ABI (include/svbasl.h).
+
+PyTorch is used for buffer ownership, streams and (multi-GPU) torch.distributed only; every kernel is in
+libsvbasl.so.  Nothing here computes on the CPU: without the library or without a CUDA device these calls
+raise.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise L.SvbAslError("no CUDA device: the ASL SVB kernels only run on the GPU (there is no CPU fallback)")
+    return L.load()
+
+
+def device_array(arr, device=None, dtype=torch.float32):
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    if torch.is_tensor(arr):
+        return arr.to(device=device, dtype=dtype).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(arr)).to(device=device, dtype=dtype).contiguous()
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def evaluate_model(model, params, tpts):
+    """Model.evaluate for the ASL plugins (aslrest.py:248-340): params list of [W,S,1] (or [P,W,S,1]),
+    tpts [W,1,B] / [1,1,B] / [n,B] -> CUDA tensor [W,S,B]."""
+    lib = _require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if isinstance(params, (list, tuple)):
+        cols = [device_array(p, dev) for p in params]
+        shape = torch.broadcast_shapes(*[c.shape for c in cols]) if cols else (1, 1, 1)
+        par = torch.stack([c.expand(shape) for c in cols], 0) if cols else torch.zeros((0,) + tuple(shape), device=dev)
+    else:
+        par = device_array(params, dev)
+    t = device_array(tpts, dev)
+    # normalise shapes to params [P, W, S] and t [Wt, B]
+    if par.ndim == 4:
+        par = par[..., 0]
+    elif par.ndim == 2:
+        par = par[..., None]
+    P, W, S = par.shape
+    if t.ndim == 3:
+        t = t.reshape(t.shape[0], t.shape[-1])
+    elif t.ndim == 1:
+        t = t.reshape(1, -1)
+    Wt, B = t.shape
+    if Wt not in (1, W):
+        raise ValueError("time points have %i rows but parameters have %i voxels" % (Wt, W))
+    n_rows = W * S
+    out = torch.empty((W, S, B), device=dev, dtype=torch.float32)
+    m, keep = model.kernel_model(lambda a: device_array(a, dev))
+    par = par.reshape(P, n_rows).contiguous()
+    t = t.contiguous()
+    L.check(lib.svbasl_evaluate(C.byref(m), par.data_ptr() if P else None, t.data_ptr(), out.data_ptr(), n_rows, S, B,
+                                Wt, _stream_ptr()))
+    del keep
+    return out
+
+
+class FusedSvb:
+    """
+    The per-iteration graph of svb's SvbFit for one shard of voxels, as one kernel launch:
+    sample -> model -> log-likelihood -> latent loss -> gradients -> Adam.
+
+    All arrays are SoA, voxel-fastest, row stride `ld`.  `state` rows: mean[P'], logvar[P'], off-diagonal
+    Cholesky rows, ARD log-phi rows (include/svbasl.h).
+    """
+
+    def __init__(self, model, data, tpts=None, *, ti=None, zoff=None, n_samples=10, batch_size=None,
+                 latent="numeric", cov_llt=False, learning_rate=0.01, seed=1, prior_types=None, prior_means=None,
+                 prior_vars=None, n_vox_global=None, vox_offset=0, halo=(0, 0), neighbours=None, ak_init=1e-5,
+                 ard_phi_max=1e6, latent_weight=1.0, device=None, adam=(0.9, 0.999, 1e-8), max_steps=100000):
+        self.lib = _require_cuda()
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.model = model
+        self.mdesc, self._keep = model.kernel_model(lambda a: device_array(a, self.dev))
+        self.data = device_array(data, self.dev)                       # [T, ld]
+        self.T, self.ld = self.data.shape
+        self.tpts = device_array(tpts, self.dev) if tpts is not None else None
+        self.ti = device_array(ti, self.dev) if ti is not None else None
+        self.zoff = device_array(zoff, self.dev) if zoff is not None else None
+        self.halo = halo
+        self.n_vox = self.ld - halo[0] - halo[1]
+        self.n_vox_global = n_vox_global or self.n_vox
+        self.vox_offset = vox_offset
+        self.S = n_samples
+        self.B = batch_size or self.T
+        self.n_batches = int(math.ceil(self.T / self.B))
+        if self.T % self.n_batches:
+            raise ValueError("time points (%i) must divide into equal strided batches (batch_size=%i)" % (self.T, self.B))
+        self.B = self.T // self.n_batches
+        P = self.lib.svbasl_model_n_params(C.byref(self.mdesc))
+        L.check(P)
+        self.P, self.N = P, P + 1
+        self.prior_types = list(prior_types)
+        self.prior_means = [float(np.mean(v)) for v in prior_means]
+        self.prior_vars = [float(v) for v in prior_vars]
+        assert len(self.prior_types) == self.N
+        self.ard = [i for i, t in enumerate(self.prior_types) if t == "A"]
+        self.mrf = [i for i, t in enumerate(self.prior_types) if t == "M"]
+        self.NL = self.N * (self.N - 1) // 2
+        self.n_state = 2 * self.N + self.NL + len(self.ard)
+        self.latent = L.LATENT_NUMERIC if (latent == "numeric" or self.mrf) else L.LATENT_ANALYTIC
+        self.cov_llt = bool(cov_llt)
+        self.lr = learning_rate
+        self.b1, self.b2, self.adam_eps = adam
+        self.seed = seed
+        self.ard_phi_max = ard_phi_max or 0.0
+        self.latent_weight = latent_weight
+        self.step_count = 0
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, device=self.dev, dtype=dt)  # noqa: E731
+        self.state = z(self.n_state, self.ld)
+        self.state_alt = z(self.n_state, self.ld) if self.mrf else None
+        self.m = z(self.n_state, self.ld)
+        self.v = z(self.n_state, self.ld)
+        steps = np.arange(1, max_steps + 1, dtype=np.float64)
+        self.lr_t_host = (learning_rate * np.sqrt(1 - self.b2 ** steps) / (1 - self.b1 ** steps)).astype(np.float32)
+        self.lr_t = device_array(self.lr_t_host, self.dev)
+        self.max_fuse = 64
+        self.cost_hist = z(max_steps + self.max_fuse, dt=torch.float64)   # summed cost of every iteration
+        self.nan_count = z(1, dt=torch.int64)
+        self.neighbours = device_array(neighbours, self.dev, torch.int32) if neighbours is not None else None
+        if self.mrf:
+            if self.neighbours is None:
+                raise ValueError("spatial prior needs a neighbour table")
+            self.log_ak = torch.full((len(self.mrf),), math.log(ak_init), device=self.dev, dtype=torch.float32)
+            self.ak_m, self.ak_v = z(len(self.mrf)), z(len(self.mrf))
+            self.ak_grad = z(L.MAX_SPATIAL, dt=torch.float64)
+        else:
+            self.log_ak = self.ak_grad = None
+        self.eps = None
+
+    # ---- descriptors ----
+    def engine_desc(self, row0=0):
+        e = L.Engine()
+        e.n_vox, e.w_begin, e.ld = self.n_vox, self.halo[0], self.ld
+        e.vox_offset = self.vox_offset - self.halo[0]
+        e.n_vox_global = self.n_vox_global
+        e.n_par, e.n_samples, e.n_batch, e.t_full = self.N, self.S, self.B, self.T
+        e.latent, e.cov_llt = self.latent, int(self.cov_llt)
+        for i in range(self.N):
+            e.prior_type[i] = L.PRIOR_CODES[self.prior_types[i]]
+            e.prior_mean[i] = self.prior_means[i]
+            e.prior_var[i] = self.prior_vars[i]
+        e.ard_phi_max, e.latent_weight = self.ard_phi_max, self.latent_weight
+        e.grad_scale = 1.0 / self.n_vox_global
+        e.state = self.state.data_ptr()
+        e.state_out = self.state_alt.data_ptr() if self.mrf else None
+        e.data = self.data.data_ptr()
+        e.tpts = self.tpts.data_ptr() if self.tpts is not None else None
+        e.ti = self.ti.data_ptr() if self.ti is not None else None
+        e.zoff = self.zoff.data_ptr() if self.zoff is not None else None
+        e.t_row0, e.t_row_stride = row0, self.n_batches
+        e.eps = self.eps.data_ptr() if self.eps is not None else None
+        e.seed = self.seed
+        e.neighbours = self.neighbours.data_ptr() if self.neighbours is not None else None
+        e.log_ak = self.log_ak.data_ptr() if self.log_ak is not None else None
+        e.ak_grad = self.ak_grad.data_ptr() if self.ak_grad is not None else None
+        return e
+
+    def adam_desc(self, n_iters=1):
+        ad = L.Adam()
+        ad.m, ad.v, ad.lr_t = self.m.data_ptr(), self.v.data_ptr(), self.lr_t.data_ptr()
+        ad.beta1, ad.beta2, ad.epsilon = self.b1, self.b2, self.adam_eps
+        ad.step0, ad.n_iters, ad.n_batches = self.step_count, n_iters, self.n_batches
+        return ad
+
+    # ---- state ----
+    def set_posterior(self, means, variances):
+        """means/variances: per internal parameter (noise last), scalar or [n_vox] -> state rows"""
+        sl = slice(self.halo[0], self.halo[0] + self.n_vox)
+        self.state.zero_()
+        for i, (mu, var) in enumerate(zip(means, variances)):
+            self.state[i, sl] = device_array(np.broadcast_to(np.asarray(mu, dtype=np.float32), (self.n_vox,)).copy(),
+                                             self.dev)
+            self.state[self.N + i, sl] = torch.log(device_array(
+                np.broadcast_to(np.asarray(var, dtype=np.float32), (self.n_vox,)).copy(), self.dev))
+        for k in range(len(self.ard)):
+            self.state[2 * self.N + self.NL + k] = math.log(1e-12)
+        self.m.zero_()
+        self.v.zero_()
+        self.cost_hist.zero_()
+        self.step_count = 0
+
+    # ---- the hot path ----
+    def step(self, n_iters=1, want_cost=True):
+        """`n_iters` fused iterations (ELBO + gradient + Adam) in ONE launch.  Returns the device tensor of
+        per-iteration summed costs (no host sync)."""
+        if self.step_count + n_iters > self.lr_t.numel():
+            raise ValueError("max_steps exceeded")
+        if self.mrf and n_iters != 1:
+            raise ValueError("spatial priors couple neighbouring voxels: one iteration per launch")
+        if n_iters > self.max_fuse:
+            raise ValueError("at most %i fused iterations per launch" % self.max_fuse)
+        e = self.engine_desc(row0=self.step_count % self.n_batches)
+        ad = self.adam_desc(n_iters)
+        if self.mrf:
+            self.ak_grad.zero_()
+        cost_ptr = self.cost_hist.data_ptr() + 8 * self.step_count if want_cost else None
+        L.check(self.lib.svbasl_step(C.byref(self.mdesc), C.byref(e), C.byref(ad), cost_ptr,
+                                     self.nan_count.data_ptr(), _stream_ptr()))
+        if self.mrf:
+            self.state, self.state_alt = self.state_alt, self.state
+            self._hyper_step()
+        self.step_count += n_iters
+        return self.cost_hist[self.step_count - n_iters:self.step_count]
+
+    def _hyper_step(self, reduce_fn=None):
+        if reduce_fn is not None:
+            reduce_fn(self.ak_grad)
+        lr_t = float(self.lr_t_host[self.step_count])
+        L.check(self.lib.svbasl_hyper_step(self.log_ak.data_ptr(), self.ak_m.data_ptr(), self.ak_v.data_ptr(),
+                                           self.ak_grad.data_ptr(), len(self.mrf), 1.0 / self.n_vox_global, lr_t,
+                                           self.b1, self.b2, self.adam_eps, _stream_ptr()))
+
+    def elbo_grad(self, step=None, row0=0):
+        """-> (cost [ld], grad [n_state, ld]) without updating anything."""
+        e = self.engine_desc(row0=row0)
+        e.state_out = None
+        cost = torch.zeros(self.ld, device=self.dev)
+        grad = torch.zeros(self.n_state, self.ld, device=self.dev)
+        if self.mrf:
+            self.ak_grad.zero_()
+        L.check(self.lib.svbasl_elbo_grad(C.byref(self.mdesc), C.byref(e), self.step_count if step is None else step,
+                                          cost.data_ptr(), grad.data_ptr(), None, _stream_ptr()))
+        return cost, grad
+
+    def model_fit(self):
+        """Prediction at the posterior mean for every time point -> [T, ld]"""
+        e = self.engine_desc()
+        out = torch.zeros(self.T, self.ld, device=self.dev)
+        L.check(self.lib.svbasl_model_fit(C.byref(self.mdesc), C.byref(e), out.data_ptr(), _stream_ptr()))
+        return out
+
+    def init_stats(self):
+        """-> mean_t, max_t, var_t, t_at_max, each [ld] (posterior initialisers, aslrest.py:461-520)"""
+        outs = [torch.zeros(self.ld, device=self.dev) for _ in range(4)]
+        tp = self.tpts
+        if tp is None:
+            tp = self.ti[:, None] + (self.zoff[None, :] if self.zoff is not None else 0.0)
+            tp = tp.expand(self.T, self.ld).contiguous()
+        L.check(self.lib.svbasl_init_stats(self.data.data_ptr(), tp.data_ptr(), self.ld, self.ld, self.T,
+                                           *[o.data_ptr() for o in outs], _stream_ptr()))
+        return outs
+
+    def fill_eps(self, step):
+        eps = torch.zeros(self.N, self.S, self.ld, device=self.dev)
+        L.check(self.lib.svbasl_fill_eps(eps.data_ptr(), self.ld, self.ld, self.vox_offset - self.halo[0], self.N,
+                                         self.S, self.seed, step, _stream_ptr()))
+        return eps
+
+    # ---- results ----
+    def posterior_mean(self):
+        """Model-space posterior means [P, n_vox] (transform applied) and internal means/variances."""
+        sl = slice(self.halo[0], self.halo[0] + self.n_vox)
+        return self.state[:self.N, sl], torch.exp(self.state[self.N:2 * self.N, sl])

@@ -63,6 +63,24 @@ class DataModel(LogBase):
         X, Y, Z = self.shape
         return np.stack([idx // (Y * Z), (idx // Z) % Y, idx % Z], axis=1).astype(np.int32)
 
+    def neighbour_table(self):
+        """6-connected neighbours inside the mask -> [W,6] int32 voxel indices (-x,+x,-y,+y,-z,+z), -1 = none.
+        The Laplacian structure of the spatial ("M") prior."""
+        coords = self.voxel_coords()
+        lut = -np.ones(self.shape, dtype=np.int64)
+        lut[coords[:, 0], coords[:, 1], coords[:, 2]] = np.arange(len(coords))
+        out = -np.ones((len(coords), 6), dtype=np.int32)
+        k = 0
+        for axis in range(3):
+            for step in (-1, 1):
+                c = coords.astype(np.int64).copy()
+                c[:, axis] += step
+                ok = (c[:, axis] >= 0) & (c[:, axis] < self.shape[axis])
+                c[~ok] = 0
+                out[:, k] = np.where(ok, lut[c[:, 0], c[:, 1], c[:, 2]], -1)
+                k += 1
+        return out
+
     def nifti_image(self, values):
         """Put per-voxel values [W] or [W,N] back in the volume -> NiftiImage"""
         values = np.asarray(values)

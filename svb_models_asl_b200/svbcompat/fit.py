@@ -1,0 +1,198 @@
+"""
+``SvbFit``: the inference engine the reference drives through ``svb.main.run`` - posterior, noise model,
+priors, cost and Adam training loop - re-built around the fused
+B200 kernel: one launch per iteration does what svb's ``sess.run(optimize)`` does for the ASL plugins.
+
+The svb source is not part of the reference tree; the conventions followed here are listed in DESIGN.md
+section 5 with a switch for each (``cov_convention``, ``ard_phi_max``, ``init_delt_var`` ...).
+
+Voxels are sharded contiguously over the ranks of ``torch.distributed`` when it is initialised (one process
+per GPU); voxel-wise priors need no data-path collective, only the scalar cost is all-reduced for reporting.
+"""
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import dist as _dist
+from .parameter import Parameter
+from .utils import LogBase
+from ..ops import FusedSvb, device_array
+
+
+def noise_parameter():
+    """svb's NoiseParameter: prior LogNormal(1, 2e5), posterior LogNormal(1, 1.02), initialised from the
+    per-voxel data variance floored at 1."""
+    def _init(_param, _t, data):
+        var = np.asarray(data).var(axis=1)
+        return np.where(var < 1, 1.0, var).astype(np.float32), None
+    return Parameter("noise", prior=_dist.LogNormal(1.0, 2e5), post=_dist.LogNormal(1.0, 1.02), post_init=_init)
+
+
+def _dist_world():
+    import torch.distributed as td
+    if td.is_available() and td.is_initialized():
+        return td.get_rank(), td.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous voxel range of `rank`: voxel order is x-slowest, so these are x-slabs."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class SvbFit(LogBase):
+    def __init__(self, data_model, fwd_model, **kwargs):
+        LogBase.__init__(self)
+        self.data_model = data_model
+        self.model = fwd_model
+        self.params = list(fwd_model.params) + [noise_parameter()]
+        self.n_params = len(self.params)
+        self.rank, self.world = _dist_world()
+        self.lo, self.hi = shard_bounds(data_model.n_nodes, self.rank, self.world)
+        self.opts = kwargs
+        self.fused = None
+
+    # ------------------------------------------------------------------
+    def _setup(self, tpts, data, batch_size, sample_size, learning_rate, epochs, **kwargs):
+        lo, hi = self.lo, self.hi
+        data = np.asarray(data, dtype=np.float32)
+        tpts = np.asarray(tpts, dtype=np.float32)
+        if tpts.ndim == 1:
+            tpts = tpts[None, :]
+        if tpts.shape[0] == 1:
+            tpts = np.broadcast_to(tpts, data.shape)
+        n_t = data.shape[1]
+        force_num = bool(kwargs.get("force_num_latent_loss", False))
+        all_normal = all(isinstance(p.prior_dist, _dist.Normal) and p.prior_type in ("N", "A") for p in self.params)
+        latent = "analytic" if (all_normal and not force_num) else "numeric"
+        prior_types = [p.prior_type for p in self.params]
+        neighbours = None
+        halo = (0, 0)
+        if "M" in prior_types:
+            if self.world > 1:
+                raise NotImplementedError("spatial priors across GPUs: use svb_models_asl_b200.spatial.ShardedSpatialFit")
+            neighbours = self.data_model.neighbour_table().T.copy()      # [6, W] local == global indices
+        n_batches = int(math.ceil(n_t / (batch_size or n_t)))
+        self.fused = FusedSvb(
+            self.model, data[lo:hi].T.copy(), tpts[lo:hi].T.copy(), n_samples=sample_size,
+            batch_size=batch_size or n_t, latent=latent, cov_llt=(kwargs.get("cov_convention", "LtL") == "LLt"),
+            learning_rate=learning_rate, seed=int(kwargs.get("seed", 1)), prior_types=prior_types,
+            prior_means=[np.mean(p.prior_dist.mean) for p in self.params],
+            prior_vars=[np.mean(p.prior_dist.var) for p in self.params],
+            n_vox_global=self.data_model.n_nodes, vox_offset=lo, halo=halo, neighbours=neighbours,
+            ak_init=float(kwargs.get("ak", 1e-5)), ard_phi_max=kwargs.get("ard_phi_max", 1e6),
+            latent_weight=float(kwargs.get("latent_weight", 1.0)), max_steps=epochs * n_batches + 1)
+        # initial posterior (svb: post_init(param, t, data) -> (mean, var) in MODEL space, mapped to internal)
+        means, variances = [], []
+        for p in self.params:
+            mean, var = None, None
+            if p.post_init is not None:
+                mean, var = p.post_init(p, tpts, data)
+                if mean is not None:
+                    mean = p.post_dist.transform.int_values(np.asarray(mean, dtype=np.float32))
+            if mean is None:
+                mean = np.full(data.shape[0], np.mean(p.post_dist.mean), dtype=np.float32)
+            if var is None:
+                var = np.full(data.shape[0], np.mean(p.post_dist.var), dtype=np.float32)
+            means.append(np.asarray(mean, dtype=np.float32)[lo:hi])
+            variances.append(np.asarray(var, dtype=np.float32)[lo:hi])
+        self.fused.set_posterior(means, variances)
+
+    # ------------------------------------------------------------------
+    def train(self, tpts, data, batch_size=None, epochs=100, learning_rate=0.1, sample_size=None, display_step=1,
+              iters_per_launch=1, **kwargs):
+        """Returns the training history dict (mean_cost per epoch; voxel cost / parameter histories when the
+        corresponding save_* option is set)."""
+        sample_size = sample_size or 5
+        self._setup(tpts, data, batch_size, sample_size, learning_rate, epochs, **kwargs)
+        f = self.fused
+        n_batches = f.n_batches
+        want_vc = bool(kwargs.get("save_cost_history", False))
+        want_ph = bool(kwargs.get("save_param_history", False))
+        hist = {"mean_cost": np.zeros(epochs + 1, dtype=np.float64)}
+        cost_dev = torch.zeros(epochs + 1, device=f.dev, dtype=torch.float64)
+        vc = torch.zeros(epochs + 1, f.n_vox, device=f.dev) if want_vc else None
+        ph = torch.zeros(epochs + 1, f.N, f.n_vox, device=f.dev) if want_ph else None
+        sl = slice(f.halo[0], f.halo[0] + f.n_vox)
+
+        def record(epoch):
+            if want_vc or epoch == 0:
+                c = self.full_cost()
+                cost_dev[epoch] = c.sum(dtype=torch.float64)
+                if want_vc:
+                    vc[epoch] = c
+            if want_ph:
+                ph[epoch] = f.state[:f.N, sl]
+
+        record(0)
+        t0 = time.time()
+        fuse = max(1, int(iters_per_launch)) if not f.mrf else 1
+        for epoch in range(epochs):
+            done = 0
+            acc = torch.zeros((), device=f.dev, dtype=torch.float64)
+            while done < n_batches:
+                k = min(fuse, n_batches - done)
+                acc = acc + f.step(k).sum()
+                done += k
+            if not want_vc:
+                cost_dev[epoch + 1] = acc / n_batches          # mean of the batch costs (no extra launch)
+            record(epoch + 1)
+            if display_step and self.rank == 0 and (epoch + 1) % max(1, display_step) == 0 and kwargs.get("log_stream"):
+                # one host sync per displayed epoch; keep display_step large for big fits
+                mc = float(cost_dev[epoch + 1]) / f.n_vox
+                kwargs["log_stream"].write(" - Epoch %04d: mean cost=%f (shard of %i voxels)\n" % (epoch + 1, mc, f.n_vox))
+        torch.cuda.synchronize()
+        self.runtime = time.time() - t0
+        total = cost_dev.clone()
+        if self.world > 1:
+            import torch.distributed as td
+            td.all_reduce(total)                                # the only collective: scalar cost, for reporting
+        hist["mean_cost"] = (total / self.data_model.n_nodes).cpu().numpy()
+        if want_vc:
+            hist["voxel_cost"] = vc.T.cpu().numpy()
+        if want_ph:
+            hist["params"] = ph.permute(2, 0, 1).cpu().numpy()  # [W, epochs+1, P']
+        hist["nan_skips"] = int(f.nan_count.item())
+        return hist
+
+    # ------------------------------------------------------------------
+    def full_cost(self):
+        """Per-voxel cost on ALL time points (what svb reports per epoch) -> [n_vox] device tensor"""
+        f = self.fused
+        saved = (f.B, f.n_batches)
+        f.B, f.n_batches = f.T, 1
+        try:
+            cost, _ = f.elbo_grad(row0=0)
+        finally:
+            f.B, f.n_batches = saved
+        return cost[f.halo[0]:f.halo[0] + f.n_vox]
+
+    def model_moments(self):
+        """Posterior mean / variance of every parameter in MODEL space (svb's model_means / model_vars:
+        exp(.) of both moments for LogNormal, |mean| for FoldedNormal) -> numpy [P', n_vox] each"""
+        mean, var = self.fused.posterior_mean()
+        mean, var = mean.clone(), var.clone()
+        for i, p in enumerate(self.params):
+            code = p.post_dist.transform.code
+            if code == _dist.XF_EXP:
+                mean[i], var[i] = torch.exp(mean[i]), torch.exp(var[i])
+            elif code == _dist.XF_ABS:
+                mean[i] = torch.abs(mean[i])
+        return mean.cpu().numpy(), var.cpu().numpy()
+
+    def model_fit(self):
+        f = self.fused
+        return f.model_fit()[:, f.halo[0]:f.halo[0] + f.n_vox].T.cpu().numpy()
+
+    def gather(self, local):
+        """Concatenate per-shard [.., n_vox] (last axis = voxels... first axis here) arrays on every rank."""
+        if self.world == 1:
+            return local
+        import torch.distributed as td
+        parts = [None] * self.world
+        td.all_gather_object(parts, local)
+        return np.concatenate(parts, axis=0)
