@@ -190,7 +190,7 @@ def main():
     fit = SvbFit(dm, model, **FIT_OPTIONS)
     fit.lo, fit.hi = 0, W                                               # every rank owns its own W voxels (weak scaling)
     fit._setup(model.tpts(), dm.data_flattened, None, FIT_OPTIONS["sample_size"], FIT_OPTIONS["learning_rate"],
-               epochs=4 * (K + WU) + 64, **FIT_OPTIONS)
+               epochs=4 * (K + WU) + 64, force_num_latent_loss=FIT_OPTIONS["force_num_latent_loss"])
     f = fit.fused
     f.n_vox_global = W * world
     n_state = f.n_state

@@ -206,7 +206,7 @@ int svbasl_evaluate(const svbasl_model *model, const float *params, const float 
         return SVBASL_E_INVALID;
     }
     EvalArgs a;
-    a.md = *model;
+    a.md = make_dev_model(*model);
     a.params = params;
     a.tpts = tpts;
     a.out = out;
@@ -224,8 +224,9 @@ static int run_step(const svbasl_model *model, const svbasl_engine *engine, cons
     if (rc) return rc;
     StepArgs a;
     memset(&a, 0, sizeof(a));
-    a.md = *model;
+    a.md = make_dev_model(*model);
     a.e = *engine;
+    a.ec = make_engine_const(*engine);
     a.update = adam ? 1 : 0;
     if (adam) {
         if (!adam->m || !adam->v || !adam->lr_t || adam->n_iters < 1 || adam->n_batches < 1) {
@@ -292,7 +293,7 @@ int svbasl_model_fit(const svbasl_model *model, const svbasl_engine *engine, flo
         return SVBASL_E_INVALID;
     }
     FitArgs a;
-    a.md = *model;
+    a.md = make_dev_model(*model);
     a.e = *engine;
     a.out = out;
     return k->fit(a, (cudaStream_t)stream);

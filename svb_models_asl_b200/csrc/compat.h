@@ -19,9 +19,13 @@ namespace svb {
 SVB_D float fexp(float x) { return __expf(x); }            // FMUL + MUFU.EX2
 SVB_D float fexp2(float x) { return exp2f(x); }
 SVB_D float flog(float x) { return __logf(x); }            // MUFU.LG2 + FMUL
-SVB_D float frcp(float x) { return __frcp_rn(x); }
+SVB_D float frcp(float x) { return __fdividef(1.0f, x); }   // MUFU.RCP (~1 ulp), no slow path
 SVB_D float fdiv(float a, float b) { return __fdividef(a, b); }
-SVB_D float fsqrt(float x) { return __fsqrt_rn(x); }
+SVB_D float fsqrt(float x) {                               // sqrt.approx: MUFU.RSQ/SQRT, no IEEE slow path
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 SVB_D void fsincos2pi(float u, float *s, float *c) { __sincosf(6.283185307179586f * u, s, c); }
 SVB_D uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 SVB_D float ferf(float x) { return erff(x); }

@@ -10,8 +10,9 @@ namespace svb {
 constexpr int kBlock = 128;
 
 struct StepArgs {
-    svbasl_model md;
+    DevModel md;
     svbasl_engine e;
+    EngineConst ec;
     svbasl_adam ad;
     int32_t update;          // 0: cost + gradient only (svbasl_elbo_grad); 1: fused Adam update (svbasl_step)
     int64_t step;            // iteration index of the first fused iteration (RNG counter / lr_t index)
@@ -22,7 +23,7 @@ struct StepArgs {
 };
 
 struct EvalArgs {
-    svbasl_model md;
+    DevModel md;
     const float *params;     // [P][n_rows]
     const float *tpts;       // [n_t_rows][B]
     float *out;              // [n_rows][B]
@@ -31,7 +32,7 @@ struct EvalArgs {
 };
 
 struct FitArgs {
-    svbasl_model md;
+    DevModel md;
     svbasl_engine e;
     float *out;              // [T][ld]
 };
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ St
     for (int it = 0; it < n_iters; ++it) {
         const int64_t step = a.step + it;
         const int row0 = (a.update && a.ad.n_batches > 1) ? (int)(step % a.ad.n_batches) : a.e.t_row0;
-        float cost = vs.elbo_grad(a.md, a.e, w, step, row0);
+        float cost = vs.elbo_grad(a.md, a.e, a.ec, w, step, row0);
         if (live) {
             if (a.cost) a.cost[w] = cost;
             if (a.grad) vs.store_grads(a.e, a.grad, w);

@@ -8,32 +8,35 @@
 //
 // Compile-time layout: the set of inferred parameters is a template bit-mask F (SVBASL_F_* flags), so the
 // parameter slots of aslrest.py:183-246 become constant register indices and unused terms vanish.
+// Everything that depends only on the options (rates, exp(tau/T1app)-1, reciprocals) is folded on the host
+// into DevModel (dev_model.h) and read straight from the constant bank.
 #pragma once
 #include "compat.h"
-#include "../../include/svbasl.h"
+#include "dev_model.h"
 
 namespace svb {
 
-// (exp(r u) - 1)/r, finite as r -> 0
-SVB_HD float em1r(float r, float u) {
-    float z = r * u;
-    return fabsf(z) < 1e-4f ? u * (1.0f + 0.5f * z) : expm1f(z) / r;
-}
-
-// d/dr of em1r(r, u) = (u exp(r u) - em1r)/r; series u^2 (1/2 + z/3 + z^2/8 + ...) where the difference cancels
-SVB_HD float dem1r(float r, float u, float e1) {
-    float z = r * u;
-    if (fabsf(z) < 0.3f) {
-        float p = 1.0f / 5040.0f * 7.0f / 8.0f;                       // 7/8! (k = 6)
-        p = p * z + 1.0f / 840.0f;
-        p = p * z + 1.0f / 144.0f;
-        p = p * z + 1.0f / 30.0f;
-        p = p * z + 0.125f;
-        p = p * z + 1.0f / 3.0f;
-        p = p * z + 0.5f;
-        return u * u * p;
-    }
-    return (u * (r * e1 + 1.0f) - e1) / r;                            // exp(r u) = r*e1 + 1
+// 1/2 (1 + erf z) and exp(-z^2)/sqrt(pi) together, branch-free.
+// erfc(|z|) = t exp(-z^2 + P(t)), t = 1/(1 + |z|/2): Chebyshev fit of Numerical Recipes (erfcc), fractional
+// error < 1.2e-7 everywhere, so the absolute error of the smoothed step is < 1e-7.  |z| is clamped at 8
+// (erfc(8) ~ 1e-29: far below float32 resolution of the step, and it keeps -z^2 away from underflow traps).
+SVB_HD void erf_step(float z, float &half_1p_erf, float &gauss) {
+    const float a = fmin2(fabsf(z), 8.0f);
+    const float t = frcp(1.0f + 0.5f * a);
+    float p = 0.17087277f;
+    p = p * t - 0.82215223f;
+    p = p * t + 1.48851587f;
+    p = p * t - 1.13520398f;
+    p = p * t + 0.27886807f;
+    p = p * t - 0.18628806f;
+    p = p * t + 0.09678418f;
+    p = p * t + 0.37409196f;
+    p = p * t + 1.00002368f;
+    p = p * t - 1.26551223f;
+    const float mz2 = -a * a;
+    const float half_erfc = 0.5f * t * fexp(mz2 + p);
+    half_1p_erf = z >= 0.0f ? 1.0f - half_erfc : half_erfc;
+    gauss = 0.5641895835477563f * fexp(mz2);
 }
 
 template <uint32_t F>
@@ -60,93 +63,83 @@ struct AslRest {
     static constexpr int I_FBLOOD = ART ? N_A : -1;
     static constexpr int I_DELTBLOOD = (ART && ATT) ? N_A + 1 : -1;
     static constexpr int P = N_A + (ART ? (1 + (ATT ? 1 : 0)) : 0);
+    static constexpr int PA = P > 0 ? P : 1;
 
     static constexpr int xf(int) { return SVBASL_XF_IDENTITY; }   // all Normal (aslrest.py:184-246)
+    static constexpr int ix(int i) { return i < 0 ? 0 : i; }
 
     struct Vox {              // per-voxel constants
         float pvgm, pvwm;
     };
 
-    // One tissue compartment's per-sample terms
+    // One tissue compartment's per-sample terms.  `k` is a copy of the constant-bank rates when T1 is fixed
+    // (the compiler keeps reading the constant bank) and per-sample values when T1 is inferred.
     struct Tissue {
+        TissueRates k;
         float delt, tdp;      // delta, fl(tau + delta)             (mask thresholds, aslrest.py:362-363)
-        float q;              // 1/T1app                            (aslrest.py:366)
-        float nk;             // -log2(e) * q : E = 2^(nk*(t-delta))
-        float Fc;             // CASL: 2*T1app*exp(-delta/t1b)      (aslrest.py:371)
-        float c1;             // CASL: exp(tau*q) - 1 ; S_post = Fc*E*c1   (aslrest.py:373, single-exp form)
-        float r;              // PASL: r = q - 1/t1b                (aslrest.py:376)
-        float erd2;           // PASL: 2*exp(r*delta)
-        float e1tau, de1tau;  // PASL: (exp(r tau)-1)/r and its r-derivative (post-bolus, aslrest.py:380)
-        float pvf;            // pv * f
-        float pv;
+        float A;              // CASL: 2*T1app*exp(-delta/t1b) (aslrest.py:371); PASL: 2*exp(r*delta)
+        float pvf, pv;        // pv*f, pv
         float dqdt1;          // dq/dt1 = -1/t1^2
     };
 
     struct Sample {
         Tissue gm, wm;
-        float fb, deltb, kc, dkc;          // arterial (aslrest.py:404-407)
-        float thr_out, ls, inv_ls, dz_in_c, dz_in_t;   // lead-in/out (aslrest.py:411-419)
+        float fb, deltb, kc, dkc;                     // arterial (aslrest.py:404-407)
+        float thr_out, inv_ls, dz_in_c, dz_in_t;     // lead-in/out (aslrest.py:411-419)
         bool leadin_ok;
     };
 
-    static SVB_HD Vox load_vox(const svbasl_model &m, int64_t w) {
+    static SVB_HD Vox load_vox(const DevModel &m, int64_t w) {
         Vox v;
         v.pvgm = m.pvgm ? m.pvgm[w] : m.pvgm_s;
         v.pvwm = m.pvwm ? m.pvwm[w] : m.pvwm_s;
         return v;
     }
 
-    static SVB_HD void prep_tissue(const svbasl_model &m, Tissue &ts, float f, float delt, float t1, float pc,
-                                   float fcalib, float pv) {
-        const float LOG2E = 1.4426950408889634f;
+    template <bool T1_SAMPLED>
+    static SVB_HD void prep_tissue(const DevModel &m, Tissue &ts, const TissueRates &fixed, float fc_pc, float f,
+                                   float delt, float t1, float pv) {
         ts.delt = delt;
         ts.tdp = m.tau + delt;
-        float q = frcp(t1) + fcalib / pc;
-        ts.q = q;
-        ts.nk = -LOG2E * q;
         ts.pv = pv;
         ts.pvf = pv * f;
-        ts.dqdt1 = -frcp(t1 * t1);
-        float inv_t1b = 1.0f / m.t1b;
-        if (CASL) {
-            ts.Fc = 2.0f * frcp(q) * fexp(-delt * inv_t1b);
-            ts.c1 = fexp(m.tau * q) - 1.0f;
+        if (T1_SAMPLED) {
+            const float it1 = frcp(t1);
+            ts.k = tissue_rates(it1 + fc_pc, m.tau, m.inv_t1b, CASL);
+            ts.dqdt1 = -it1 * it1;
         } else {
-            ts.r = q - inv_t1b;
-            ts.erd2 = 2.0f * fexp(ts.r * delt);
-            ts.e1tau = em1r(ts.r, m.tau);
-            ts.de1tau = dem1r(ts.r, m.tau, ts.e1tau);
+            ts.k = fixed;
+            ts.dqdt1 = 0.0f;
         }
+        ts.A = CASL ? ts.k.two_iq * fexp(-delt * m.inv_t1b) : 2.0f * fexp(ts.k.r * delt);
     }
 
     // x[P]: model-space parameter values for this sample
-    static SVB_HD Sample prep_sample(const svbasl_model &m, const Vox &v, const float *x) {
+    static SVB_HD Sample prep_sample(const DevModel &m, const Vox &v, const float *x) {
         Sample s;
         if (TISS) {
-            float t1 = T1 ? x[I_T1 < 0 ? 0 : I_T1] : m.t1;
-            float delt = ATT ? x[I_DELT < 0 ? 0 : I_DELT] : m.att;
-            prep_tissue(m, s.gm, x[I_FTISS < 0 ? 0 : I_FTISS], delt, t1, m.pc, m.fcalib, v.pvgm);
+            const float delt = ATT ? x[ix(I_DELT)] : m.att;
+            prep_tissue<T1>(m, s.gm, m.gm, m.fc_pc, x[ix(I_FTISS)], delt, T1 ? x[ix(I_T1)] : 0.0f, v.pvgm);
             if (INCWM) {
-                float t1wm = (I_T1WM >= 0) ? x[I_T1WM < 0 ? 0 : I_T1WM] : m.t1wm;
-                float fwm = INFWM ? x[I_FWM < 0 ? 0 : I_FWM] : m.fwm;
-                float dwm = (I_DELTWM >= 0) ? x[I_DELTWM < 0 ? 0 : I_DELTWM] : m.attwm;
-                prep_tissue(m, s.wm, fwm, dwm, t1wm, m.pcwm, m.fcalibwm, v.pvwm);
+                const float fwm = INFWM ? x[ix(I_FWM)] : m.fwm;
+                const float dwm = (I_DELTWM >= 0) ? x[ix(I_DELTWM)] : m.attwm;
+                prep_tissue<(I_T1WM >= 0)>(m, s.wm, m.wm, m.fc_pc_wm, fwm, dwm, (I_T1WM >= 0) ? x[ix(I_T1WM)] : 0.0f,
+                                           v.pvwm);
             }
         }
         if (ART) {
-            s.fb = x[I_FBLOOD < 0 ? 0 : I_FBLOOD];
-            float db = (I_DELTBLOOD >= 0) ? x[I_DELTBLOOD < 0 ? 0 : I_DELTBLOOD] : m.artt;   // Appendix C5
+            s.fb = x[ix(I_FBLOOD)];
+            const float db = (I_DELTBLOOD >= 0) ? x[ix(I_DELTBLOOD)] : m.artt;
             s.deltb = db;
-            float inv_t1b = 1.0f / m.t1b;
-            s.kc = CASL ? 2.0f * fexp(-db * inv_t1b) : 0.0f;
-            s.dkc = -s.kc * inv_t1b;
-            s.thr_out = db + 0.5f * m.tau;
-            s.ls = fmin2(db, m.leadscale);
-            s.leadin_ok = s.ls > 0.0f;
-            float ils = frcp(s.leadin_ok ? s.ls : 1.0f);
+            s.kc = CASL ? 2.0f * fexp(-db * m.inv_t1b) : 0.0f;
+            s.dkc = -s.kc * m.inv_t1b;
+            s.thr_out = db + m.half_tau;
+            const float ls = fmin2(db, m.leadscale);
+            s.leadin_ok = ls > 0.0f;
+            // tf.minimum routes the gradient to deltblood when it is the smaller argument: z_in = t/db - 1
+            const bool own = db <= m.leadscale;
+            const float ils = own ? frcp(s.leadin_ok ? ls : 1.0f) : m.inv_leadscale;
             s.inv_ls = ils;
-            // d z_in / d deltb = -1/ls when deltb > leadscale; -(t)/deltb^2 when the minimum selects deltb
-            bool own = db <= m.leadscale;
             s.dz_in_c = own ? 0.0f : -ils;
             s.dz_in_t = own ? -ils * ils : 0.0f;
         }
@@ -154,94 +147,88 @@ struct AslRest {
     }
 
     // value S (per unit pv*f) and derivatives wrt delta and q of one tissue compartment at time t
-    static SVB_HD void tissue_eval(const svbasl_model &m, const Tissue &ts, float t, float &S, float &dSdd,
-                                   float &dSdq) {
-        bool post = t > ts.tdp;
-        bool during = (t > ts.delt) && !post;
-        float u = t - ts.delt;
-        float inv_t1b = 1.0f / m.t1b;
+    template <bool WANT_Q>
+    static SVB_HD void tissue_eval(const DevModel &m, const Tissue &ts, float t, float &S, float &dSdd, float &dSdq) {
+        const bool post = t > ts.tdp;
+        const bool during = (t > ts.delt) && !post;
+        const float u = t - ts.delt;
         if (CASL) {
-            float E = fexp2(u * ts.nk);
-            float FE = ts.Fc * E;
-            float Sd = ts.Fc - FE;
-            float Sp = FE * ts.c1;
-            float dd = -Sd * inv_t1b - FE * ts.q;
-            float dp = Sp * (ts.q - inv_t1b);
+            const float E = fexp2(u * ts.k.nk);            // exp(-(t-delta)/T1app)
+            const float FE = ts.A * E;
+            const float Sd = ts.A - FE;                    // aslrest.py:372
+            const float Sp = FE * ts.k.c1;                 // aslrest.py:373 with exp(tau q) folded into c1
+            const float dd = -Sd * m.inv_t1b - FE * ts.k.q;
+            const float dp = Sp * (ts.k.q - m.inv_t1b);
             S = post ? Sp : (during ? Sd : 0.0f);
             dSdd = post ? dp : (during ? dd : 0.0f);
-            if (T1) {
-                float iq = frcp(ts.q);
-                float qd = FE * u - Sd * iq;
-                float qp = Sp * (m.tau * (ts.c1 + 1.0f) * frcp(ts.c1) - u - iq);
+            if (WANT_Q) {
+                const float qd = FE * u - Sd * ts.k.iq;
+                const float qp = Sp * (ts.k.tc1 - u - ts.k.iq);
                 dSdq = post ? qp : (during ? qd : 0.0f);
             }
         } else {
             // factor*(exp(r t) - exp(r delt)) = 2 exp(-t q) exp(r delt) * (exp(r u) - 1)/r, which (unlike the
             // reference's float32 form) stays accurate when T1app is close to t1b (r -> 0)
-            (void)inv_t1b;
-            float Be2 = fexp2(t * ts.nk) * ts.erd2;        // 2 exp(-t/T1app) exp(r delt)
-            float e1u = em1r(ts.r, u);
-            float Sd = Be2 * e1u;
-            float Sp = Be2 * ts.e1tau;
+            const float Be2 = fexp2(t * ts.k.nk) * ts.A;   // 2 exp(-t/T1app) exp(r delt)
+            const float e1u = em1r(ts.k.r, u);
+            const float Sd = Be2 * e1u;                    // aslrest.py:379
+            const float Sp = Be2 * ts.k.e1tau;             // aslrest.py:380
             S = post ? Sp : (during ? Sd : 0.0f);
-            dSdd = post ? ts.r * Sp : (during ? -Be2 : 0.0f);
-            if (T1) {
-                float qd = Be2 * dem1r(ts.r, u, e1u) - u * Sd;
-                float qp = Be2 * ts.de1tau - u * Sp;
+            dSdd = post ? ts.k.r * Sp : (during ? -Be2 : 0.0f);
+            if (WANT_Q) {
+                const float qd = Be2 * dem1r(ts.k.r, u, e1u) - u * Sd;
+                const float qp = Be2 * ts.k.de1tau - u * Sp;
                 dSdq = post ? qp : (during ? qd : 0.0f);
             }
         }
     }
 
     // prediction at time t and d pred / d x[p]
-    static SVB_HD void eval(const svbasl_model &m, const Sample &s, float t, float &pred, float *d) {
+    static SVB_HD void eval(const DevModel &m, const Sample &s, float t, float &pred, float *d) {
         pred = 0.0f;
         if (TISS) {
             float S, dd, dq = 0.0f;
-            tissue_eval(m, s.gm, t, S, dd, dq);
+            tissue_eval<T1>(m, s.gm, t, S, dd, dq);
             pred = s.gm.pvf * S;
-            d[I_FTISS < 0 ? 0 : I_FTISS] = s.gm.pv * S;
-            if (ATT) d[I_DELT < 0 ? 0 : I_DELT] = s.gm.pvf * dd;
-            if (T1) d[I_T1 < 0 ? 0 : I_T1] = s.gm.pvf * dq * s.gm.dqdt1;
+            d[ix(I_FTISS)] = s.gm.pv * S;
+            if (ATT) d[ix(I_DELT)] = s.gm.pvf * dd;
+            if (T1) d[ix(I_T1)] = s.gm.pvf * dq * s.gm.dqdt1;
             if (INCWM) {
                 float Sw, ddw, dqw = 0.0f;
-                tissue_eval(m, s.wm, t, Sw, ddw, dqw);
+                tissue_eval<(I_T1WM >= 0)>(m, s.wm, t, Sw, ddw, dqw);
                 pred += s.wm.pvf * Sw;
-                if (INFWM) d[I_FWM < 0 ? 0 : I_FWM] = s.wm.pv * Sw;
-                if (I_DELTWM >= 0) d[I_DELTWM < 0 ? 0 : I_DELTWM] = s.wm.pvf * ddw;
-                if (I_T1WM >= 0) d[I_T1WM < 0 ? 0 : I_T1WM] = s.wm.pvf * dqw * s.wm.dqdt1;
+                if (INFWM) d[ix(I_FWM)] = s.wm.pv * Sw;
+                if (I_DELTWM >= 0) d[ix(I_DELTWM)] = s.wm.pvf * ddw;
+                if (I_T1WM >= 0) d[ix(I_T1WM)] = s.wm.pvf * dqw * s.wm.dqdt1;
             } else if (I_T1WM >= 0) {
-                d[I_T1WM < 0 ? 0 : I_T1WM] = 0.0f;
+                d[ix(I_T1WM)] = 0.0f;
             }
         } else {
-            if (T1) d[I_T1 < 0 ? 0 : I_T1] = 0.0f;          // artonly + infert1: parameter exists, unused
-            if (I_T1WM >= 0) d[I_T1WM < 0 ? 0 : I_T1WM] = 0.0f;
+            if (T1) d[ix(I_T1)] = 0.0f;                    // artonly + infert1: parameter exists, unused
+            if (I_T1WM >= 0) d[ix(I_T1WM)] = 0.0f;
         }
         if (ART) {
-            const float INV_SQRT_PI = 0.5641895835477563f;
-            float inv_t1b = 1.0f / m.t1b;
-            float inv_LS = 1.0f / m.leadscale;
-            float kc = CASL ? s.kc : 2.0f * fexp(-t * inv_t1b);
-            float dkc = CASL ? s.dkc : 0.0f;
-            bool leadout = t > s.thr_out;
-            bool active = leadout || s.leadin_ok;
-            float u = t - s.deltb;
-            float z = leadout ? -(u - m.tau) * inv_LS : u * s.inv_ls;
-            float dz = leadout ? inv_LS : (s.dz_in_c + s.dz_in_t * t);
-            float h = 0.5f * (1.0f + ferf(z));
-            float g = INV_SQRT_PI * fexp(-z * z);
-            float A = active ? kc * h : 0.0f;
-            float dA = active ? (dkc * h + kc * g * dz) : 0.0f;
+            const float kc = CASL ? s.kc : 2.0f * fexp(-t * m.inv_t1b);     // aslrest.py:404-407
+            const float dkc = CASL ? s.dkc : 0.0f;
+            const bool leadout = t > s.thr_out;                             // aslrest.py:411
+            const bool active = leadout || s.leadin_ok;                     // aslrest.py:419
+            const float u = t - s.deltb;
+            const float z = leadout ? -(u - m.tau) * m.inv_leadscale : u * s.inv_ls;   // aslrest.py:422-423
+            const float dz = leadout ? m.inv_leadscale : (s.dz_in_c + s.dz_in_t * t);
+            float h, g;
+            erf_step(z, h, g);
+            const float A = active ? kc * h : 0.0f;
+            const float dA = active ? (dkc * h + kc * g * dz) : 0.0f;
             pred += s.fb * A;
-            d[I_FBLOOD < 0 ? 0 : I_FBLOOD] = A;
-            if (I_DELTBLOOD >= 0) d[I_DELTBLOOD < 0 ? 0 : I_DELTBLOOD] = s.fb * dA;
+            d[ix(I_FBLOOD)] = A;
+            if (I_DELTBLOOD >= 0) d[ix(I_DELTBLOOD)] = s.fb * dA;
         }
     }
 
     // forward value only (Model.evaluate)
-    static SVB_HD float predict(const svbasl_model &m, const Vox &v, const float *x, float t) {
+    static SVB_HD float predict(const DevModel &m, const Vox &v, const float *x, float t) {
         Sample s = prep_sample(m, v, x);
-        float pred, d[P > 0 ? P : 1];
+        float pred, d[PA];
         eval(m, s, t, pred, d);
         return pred;
     }
@@ -249,19 +236,19 @@ struct AslRest {
     // Visit every time point of the batch.  Acc supplies: static NB (compile-time batch size, 0 = dynamic),
     // n(), time(b) and add(b, pred, d).
     template <class Acc>
-    static SVB_HD void run(const svbasl_model &m, const Vox &v, const float *x, Acc &acc) {
+    static SVB_HD void run(const DevModel &m, const Vox &v, const float *x, Acc &acc) {
         Sample s = prep_sample(m, v, x);
         if (Acc::NB > 0) {
 #pragma unroll
             for (int b = 0; b < (Acc::NB > 0 ? Acc::NB : 1); ++b) {
-                float pred, d[P > 0 ? P : 1];
+                float pred, d[PA];
                 eval(m, s, acc.time(b), pred, d);
                 acc.add(b, pred, d);
             }
         } else {
             const int nb = acc.n();
             for (int b = 0; b < nb; ++b) {
-                float pred, d[P > 0 ? P : 1];
+                float pred, d[PA];
                 eval(m, s, acc.time(b), pred, d);
                 acc.add(b, pred, d);
             }

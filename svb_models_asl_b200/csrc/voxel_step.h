@@ -12,7 +12,7 @@
 #pragma once
 #include "compat.h"
 #include "philox.h"
-#include "../../include/svbasl.h"
+#include "dev_model.h"
 
 namespace svb {
 
@@ -66,6 +66,26 @@ struct BatchAcc {
         for (int p = 0; p < P; ++p) G[p] += r * d[p];
     }
 };
+
+// Engine-level constants folded on the host (no divisions / logs per voxel)
+struct EngineConst {
+    float pinv[SVBASL_MAX_PAR];     // 1 / prior variance
+    float plog[SVBASL_MAX_PAR];     // log prior variance
+    float t_full, scale, inv_s;     // T, T/B, 1/S
+};
+
+inline EngineConst make_engine_const(const svbasl_engine &e) {
+    EngineConst c;
+    for (int i = 0; i < SVBASL_MAX_PAR; ++i) {
+        const bool ok = i < e.n_par && e.prior_var[i] > 0.0f;
+        c.pinv[i] = ok ? 1.0f / e.prior_var[i] : 0.0f;
+        c.plog[i] = ok ? logf(e.prior_var[i]) : 0.0f;
+    }
+    c.t_full = (float)e.t_full;
+    c.scale = (float)e.t_full / (float)e.n_batch;
+    c.inv_s = 1.0f / (float)e.n_samples;
+    return c;
+}
 
 SVB_HD constexpr int popc_below(uint32_t mask, int i) {     // set bits of mask strictly below bit i
     int n = 0;
@@ -143,10 +163,11 @@ struct VoxelStep {
     }
 
     // Cost of this voxel for one batch, gradients left in g_*.  Returns the un-scaled cost.
-    SVB_HD float elbo_grad(const svbasl_model &md, const svbasl_engine &e, int64_t w, int64_t step, int row0) {
+    SVB_HD float elbo_grad(const DevModel &md, const svbasl_engine &e, const EngineConst &ec, int64_t w, int64_t step,
+                           int row0) {
         const int S = e.n_samples;
-        const float Tf = (float)e.t_full;
-        const float scale = Tf / (float)e.n_batch;
+        const float Tf = ec.t_full;
+        const float scale = ec.scale;
         const float lw = e.latent_weight;
         const bool numeric = (e.latent == SVBASL_LATENT_NUMERIC);
         typename M::Vox vox = M::load_vox(md, w);
@@ -167,8 +188,8 @@ struct VoxelStep {
                 plog[i] = -flog(phi);
                 phi_live[i] = clipped ? 0.0f : 1.0f;
             } else {
-                pinv[i] = 1.0f / e.prior_var[i];
-                plog[i] = flog(e.prior_var[i]);
+                pinv[i] = ec.pinv[i];
+                plog[i] = ec.plog[i];
                 phi_live[i] = 0.0f;
             }
         }
@@ -279,7 +300,7 @@ struct VoxelStep {
                 for (int j = 0; j <= i; ++j) a_L[tri(i, j)] += g[i] * eps[j];
             }
         }
-        const float invS = 1.0f / (float)S;
+        const float invS = ec.inv_s;
         cost *= invS;
 #pragma unroll
         for (int i = 0; i < N; ++i) { a_mu[i] *= invS; a_phi[i] *= invS; }
@@ -367,7 +388,7 @@ struct VoxelStep {
         float vv = ad.beta2 * (*v) + (1.0f - ad.beta2) * g * g;
         *m = mm;
         *v = vv;
-        return x - lr_t * mm / (fsqrt(vv) + ad.epsilon);
+        return x - lr_t * fdiv(mm, fsqrt(vv) + ad.epsilon);
     }
 
     // tf.train.AdamOptimizer step on this voxel's rows; moments streamed through global memory.

@@ -15,6 +15,8 @@ template <class M, int NBT, uint32_t MRFMASK>
 static int run_step(const svbasl_model *md, const svbasl_engine *e, const svbasl_adam *ad, int64_t step0, float *cost,
                     float *grad, double *cost_sum, double *ak_grad) {
     const int n_iters = ad ? ad->n_iters : 1;
+    const DevModel dm = make_dev_model(*md);
+    const EngineConst ec = make_engine_const(*e);
     for (int64_t local = 0; local < e->n_vox; ++local) {
         const int64_t w = e->w_begin + local;
         VoxelStep<M, NBT, MRFMASK> vs;
@@ -22,7 +24,7 @@ static int run_step(const svbasl_model *md, const svbasl_engine *e, const svbasl
         for (int it = 0; it < n_iters; ++it) {
             const int64_t step = (ad ? ad->step0 : step0) + it;
             const int row0 = (ad && ad->n_batches > 1) ? (int)(step % ad->n_batches) : e->t_row0;
-            float c = vs.elbo_grad(*md, *e, w, step, row0);
+            float c = vs.elbo_grad(dm, *e, ec, w, step, row0);
             if (cost) cost[w] = c;
             if (grad) vs.store_grads(*e, grad, w);
             if (ad) {
@@ -41,12 +43,13 @@ template <class M>
 static int run_eval(const svbasl_model *md, const float *params, const float *tpts, float *out, int64_t n_rows,
                     int n_samples, int n_batch, int64_t n_t_rows) {
     const int64_t rows_per_t = n_rows / n_t_rows;
+    const DevModel dm = make_dev_model(*md);
     for (int64_t row = 0; row < n_rows; ++row) {
         float x[M::P > 0 ? M::P : 1];
         for (int p = 0; p < M::P; ++p) x[p] = params[(int64_t)p * n_rows + row];
-        typename M::Vox vx = M::load_vox(*md, row / n_samples);
+        typename M::Vox vx = M::load_vox(dm, row / n_samples);
         for (int b = 0; b < n_batch; ++b)
-            out[row * n_batch + b] = M::predict(*md, vx, x, tpts[(row / rows_per_t) * n_batch + b]);
+            out[row * n_batch + b] = M::predict(dm, vx, x, tpts[(row / rows_per_t) * n_batch + b]);
     }
     return 0;
 }
