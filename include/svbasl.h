@@ -33,6 +33,8 @@ extern "C" {
 #define SVBASL_ABI_VERSION 1
 #define SVBASL_MAX_PAR 10          /* P' = model parameters + noise */
 #define SVBASL_MAX_SPATIAL 4
+#define SVBASL_NN_HIDDEN 10        /* aslnn.py:238-240: 2 -> 10 -> 10 -> 1 */
+#define SVBASL_NN_NWEIGHTS 151     /* W0[2][10] b0[10] W1[10][10] b1[10] W2[10] b2[1] */
 
 /* error codes */
 #define SVBASL_OK 0
@@ -86,8 +88,9 @@ typedef struct svbasl_model {
     float conv_dt, conv_tmax;
     int32_t conv_nt;
     float s_fixed, sp_fixed;       /* used when !DISP_INFER (aslrest_disp.py:88-90) */
-    /* aslnn.py:229-241: 2->10 tanh ->10 tanh ->1, packed W0[2][10] b0[10] W1[10][10] b1[10] W2[10] b2[1] */
-    const float *nn_weights;       /* device, 151 floats */
+    /* aslnn.py:229-241: 2->10 tanh ->10 tanh ->1, packed W0[2][10] b0[10] W1[10][10] b1[10] W2[10] b2[1]
+     * in the layout of the reference's weights%i.npy / biases%i.npy files (aslnn.py:326-340) */
+    const float *nn_weights;       /* HOST pointer, SVBASL_NN_NWEIGHTS floats; copied into the kernel arguments */
 } svbasl_model;
 
 /* Inference-engine description for one shard of voxels: what svb's SvbFit builds around the
@@ -128,8 +131,11 @@ typedef struct svbasl_engine {
     const float *eps;
     uint64_t seed;
     /* spatial prior ("M"): neighbour table [6][ld] of LOCAL voxel indices, -1 = none.  The local arrays
-     * cover a contiguous global range [lower halo | owned | upper halo]; halo voxels are only read */
+     * cover a contiguous global range [lower halo | owned | upper halo]; halo voxels are only read.
+     * spatial_samples [n spatial params][S][ld]: theta samples of the spatially-regularised parameters of every
+     * local voxel (halo included) for this step, written by svbasl_sample_spatial() before the step */
     const int32_t *neighbours;
+    const float *spatial_samples;
     const float *log_ak;           /* [n spatial params] device */
     double *ak_grad;               /* [n spatial params] device accumulators: d(sum cost)/d(log ak) */
 } svbasl_engine;
@@ -171,6 +177,11 @@ int svbasl_elbo_grad(const svbasl_model *model, const svbasl_engine *engine, int
  * nan_count device int64[1] counts voxels whose update was skipped for non-finite gradients (may be NULL). */
 int svbasl_step(const svbasl_model *model, const svbasl_engine *engine, const svbasl_adam *adam,
                 double *cost_sum, long long *nan_count, void *stream);
+
+/* Pre-pass of a step with spatial priors: out [n spatial params][S][ld] = theta_{p,s} = mu_p + (L eps_s)_p for
+ * every local voxel in [0, n_local) (owned + halo), from engine->state and the step's draws (engine->eps or the
+ * Philox stream of `step`).  Neighbours then read each other's samples instead of rebuilding them. */
+int svbasl_sample_spatial(const svbasl_engine *engine, int64_t n_local, int64_t step, float *out, void *stream);
 
 /* Adam update of the global spatial-precision hyper-parameters from ak_grad (after any allreduce). */
 int svbasl_hyper_step(float *log_ak, float *m, float *v, const double *ak_grad, int32_t n, float grad_scale,

@@ -51,7 +51,7 @@ class Engine(C.Structure):
         ("data", C.c_void_p), ("tpts", C.c_void_p), ("ti", C.c_void_p), ("zoff", C.c_void_p),
         ("t_row0", C.c_int32), ("t_row_stride", C.c_int32),
         ("eps", C.c_void_p), ("seed", C.c_uint64),
-        ("neighbours", C.c_void_p), ("log_ak", C.c_void_p), ("ak_grad", C.c_void_p),
+        ("neighbours", C.c_void_p), ("spatial_samples", C.c_void_p), ("log_ak", C.c_void_p), ("ak_grad", C.c_void_p),
     ]
 
 
@@ -78,6 +78,7 @@ _EXPORTS = {
                                    C.c_void_p, C.c_void_p]),
     "svbasl_step": (C.c_int, [C.POINTER(Model), C.POINTER(Engine), C.POINTER(Adam), C.c_void_p, C.c_void_p,
                               C.c_void_p]),
+    "svbasl_sample_spatial": (C.c_int, [C.POINTER(Engine), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "svbasl_hyper_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
                                     C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "svbasl_fill_eps": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_uint64,

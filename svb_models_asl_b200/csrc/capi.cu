@@ -27,11 +27,13 @@ static uint32_t canonical_flags(const svbasl_model *m) {
         if (f & SVBASL_F_ARTONLY) f |= SVBASL_F_INFERART;                      // aslrest.py:137-138
         if (f & SVBASL_F_INFERWM) f |= SVBASL_F_INCWM;                        // aslrest.py:103-105
         if (f & SVBASL_F_ARTONLY) f &= ~(uint32_t)(SVBASL_F_INCWM | SVBASL_F_INFERWM);
+    } else if (m->kind == SVBASL_MODEL_ASLNN) {
+        f = 0;
     }
     return f;
 }
 
-static const KernelEntry *find_entry(const svbasl_model *m, int nbt, uint32_t mrfmask, bool want_eval) {
+static const KernelEntry *find_entry(const svbasl_model *m, int nbt, bool want_eval) {
     const uint32_t f = canonical_flags(m);
     const KernelEntry *fallback = nullptr;
     for (int g = 0; g < kNumEntryGroups; ++g) {
@@ -41,7 +43,6 @@ static const KernelEntry *find_entry(const svbasl_model *m, int nbt, uint32_t mr
                 if (e->eval) return e;
                 continue;
             }
-            if (e->mrfmask != mrfmask) continue;
             if (e->nbt == nbt) return e;
             if (e->nbt == 0) fallback = e;
         }
@@ -72,16 +73,20 @@ static int validate(const svbasl_model *m, const svbasl_engine *e, const KernelE
         set_error("spatial (M) priors need the sample-based latent loss");
         return SVBASL_E_INVALID;
     }
-    if (mask && (!e->neighbours || !e->log_ak)) { set_error("spatial prior without neighbours/log_ak"); return SVBASL_E_INVALID; }
-    const KernelEntry *k = find_entry(m, e->n_batch, mask, false);
+    if (mask && (!e->neighbours || !e->log_ak || !e->spatial_samples)) {
+        set_error("spatial prior without neighbours / log_ak / spatial_samples (call svbasl_sample_spatial first)");
+        return SVBASL_E_INVALID;
+    }
+    const KernelEntry *k = find_entry(m, e->n_batch, false);
     if (!k) {
-        set_error("no kernel compiled for model kind=%d flags=0x%x spatial-mask=0x%x", m->kind, canonical_flags(m), mask);
+        set_error("no kernel compiled for model kind=%d flags=0x%x", m->kind, canonical_flags(m));
         return SVBASL_E_UNSUPPORTED;
     }
     if (e->n_par != k->n_params + 1) {
         set_error("engine n_par=%d but the model has %d parameters (+1 noise)", e->n_par, k->n_params);
         return SVBASL_E_INVALID;
     }
+    if (m->kind == SVBASL_MODEL_ASLNN && !m->nn_weights) { set_error("aslnn needs nn_weights"); return SVBASL_E_INVALID; }
     if (m->kind == SVBASL_MODEL_ASLREST && (canonical_flags(m) & SVBASL_F_INFERT1) == 0 && !(m->t1 > 0.0f)) {
         set_error("t1 must be positive");
         return SVBASL_E_INVALID;
@@ -95,15 +100,13 @@ __global__ void fill_eps_kernel(float *eps, int64_t n_vox, int64_t ld, int64_t v
                                 uint64_t seed, int64_t step) {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_vox) return;
-    const int groups = (n_samples + 3) / 4;
-    for (int j = 0; j < n_par; ++j) {
-        for (int sg = 0; sg < groups; ++sg) {
-            float n4[4];
-            normal4(seed, step, vox_offset + w, j, sg, n4);
-            for (int k = 0; k < 4; ++k) {
-                const int s = 4 * sg + k;
-                if (s < n_samples) eps[((int64_t)j * n_samples + s) * ld + w] = n4[k];
-            }
+    const uint32_t key = rng_key(seed, step);
+    for (int s = 0; s < n_samples; ++s) {
+        for (int k = 0; 2 * k < n_par; ++k) {
+            float n0, n1;
+            normal2(key, vox_offset + w, s, k, n0, n1);
+            eps[((int64_t)(2 * k) * n_samples + s) * ld + w] = n0;
+            if (2 * k + 1 < n_par) eps[((int64_t)(2 * k + 1) * n_samples + s) * ld + w] = n1;
         }
     }
 }
@@ -174,7 +177,7 @@ int svbasl_abi_version(void) { return SVBASL_ABI_VERSION; }
 
 int svbasl_model_n_params(const svbasl_model *model) {
     if (!model) { set_error("null model"); return SVBASL_E_INVALID; }
-    const KernelEntry *k = find_entry(model, 0, 0, true);
+    const KernelEntry *k = find_entry(model, 0, true);
     if (!k) {
         set_error("no kernel compiled for model kind=%d flags=0x%x", model->kind, canonical_flags(model));
         return SVBASL_E_UNSUPPORTED;
@@ -195,7 +198,7 @@ int svbasl_n_state(const svbasl_model *model, const svbasl_engine *engine) {
 int svbasl_evaluate(const svbasl_model *model, const float *params, const float *tpts, float *out, int64_t n_rows,
                     int32_t n_samples, int32_t n_batch, int64_t n_t_rows, void *stream) {
     if (!model || !tpts || !out) { set_error("null argument"); return SVBASL_E_INVALID; }
-    const KernelEntry *k = find_entry(model, 0, 0, true);
+    const KernelEntry *k = find_entry(model, 0, true);
     if (!k) {
         set_error("no kernel compiled for model kind=%d flags=0x%x", model->kind, canonical_flags(model));
         return SVBASL_E_UNSUPPORTED;
@@ -228,6 +231,12 @@ static int run_step(const svbasl_model *model, const svbasl_engine *engine, cons
     a.e = *engine;
     a.ec = make_engine_const(*engine);
     a.update = adam ? 1 : 0;
+    {
+        const int n = engine->n_par;
+        int n_ard = 0;
+        for (int i = 0; i < n; ++i) n_ard += (engine->prior_type[i] == SVBASL_PRIOR_ARD);
+        a.n_state = 2 * n + n * (n - 1) / 2 + n_ard;
+    }
     if (adam) {
         if (!adam->m || !adam->v || !adam->lr_t || adam->n_iters < 1 || adam->n_batches < 1) {
             set_error("bad adam descriptor");
@@ -259,6 +268,23 @@ int svbasl_step(const svbasl_model *model, const svbasl_engine *engine, const sv
     return run_step(model, engine, adam, 0, nullptr, nullptr, cost_sum, nan_count, stream);
 }
 
+int svbasl_sample_spatial(const svbasl_engine *engine, int64_t n_local, int64_t step, float *out, void *stream) {
+    if (!engine || !out || !engine->state || n_local < 0 || n_local > engine->ld || engine->n_par < 1 ||
+        engine->n_par > SVBASL_MAX_PAR || engine->n_samples < 1) {
+        set_error("bad sample_spatial arguments");
+        return SVBASL_E_INVALID;
+    }
+    if (n_local == 0 || mrf_mask(engine) == 0) return 0;
+    SpatialArgs a;
+    a.e = *engine;
+    a.ec = make_engine_const(*engine);
+    a.n_local = n_local;
+    a.step = step;
+    a.out = out;
+    spatial_sample_kernel<<<(unsigned)((n_local + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("spatial_sample_kernel");
+}
+
 int svbasl_hyper_step(float *log_ak, float *m, float *v, const double *ak_grad, int32_t n, float grad_scale, float lr_t,
                       float beta1, float beta2, float epsilon, void *stream) {
     if (!log_ak || !m || !v || !ak_grad || n < 1 || n > SVBASL_MAX_SPATIAL) { set_error("bad hyper_step arguments"); return SVBASL_E_INVALID; }
@@ -286,7 +312,7 @@ int svbasl_init_stats(const float *data, const float *tpts, int64_t n_vox, int64
 
 int svbasl_model_fit(const svbasl_model *model, const svbasl_engine *engine, float *out, void *stream) {
     if (!model || !engine || !out) { set_error("null argument"); return SVBASL_E_INVALID; }
-    const KernelEntry *k = find_entry(model, 0, 0, true);
+    const KernelEntry *k = find_entry(model, 0, true);
     if (!k) { set_error("no kernel compiled for model kind=%d flags=0x%x", model->kind, canonical_flags(model)); return SVBASL_E_UNSUPPORTED; }
     if (engine->n_par != k->n_params + 1 || !engine->state || (!engine->tpts && !engine->ti)) {
         set_error("bad engine descriptor for model_fit");

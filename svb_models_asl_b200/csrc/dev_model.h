@@ -58,6 +58,12 @@ SVB_HD TissueRates tissue_rates(float q, float tau, float inv_t1b, bool casl) {
     return k;
 }
 
+struct NNWeights {                    // aslnn.py:238-240, row-major as in the .npy files
+    float w0[2][SVBASL_NN_HIDDEN], b0[SVBASL_NN_HIDDEN];
+    float w1[SVBASL_NN_HIDDEN][SVBASL_NN_HIDDEN], b1[SVBASL_NN_HIDDEN];
+    float w2[SVBASL_NN_HIDDEN], b2;
+};
+
 struct DevModel {
     int32_t kind;
     uint32_t flags;
@@ -71,7 +77,7 @@ struct DevModel {
     float conv_dt, conv_tmax;
     int32_t conv_nt;
     float s_fixed, sp_fixed;
-    const float *nn_weights;
+    NNWeights nn;
 };
 
 // host side: fold the options (runs in capi.cu / tests' host build, never per voxel)
@@ -102,7 +108,18 @@ inline DevModel make_dev_model(const svbasl_model &m) {
     d.conv_nt = m.conv_nt;
     d.s_fixed = m.s_fixed;
     d.sp_fixed = m.sp_fixed;
-    d.nn_weights = m.nn_weights;
+    if (m.kind == SVBASL_MODEL_ASLNN && m.nn_weights) {
+        const float *p = m.nn_weights;
+        const int H = SVBASL_NN_HIDDEN;
+        for (int i = 0; i < 2; ++i) for (int j = 0; j < H; ++j) d.nn.w0[i][j] = *p++;
+        for (int j = 0; j < H; ++j) d.nn.b0[j] = *p++;
+        for (int i = 0; i < H; ++i) for (int j = 0; j < H; ++j) d.nn.w1[i][j] = *p++;
+        for (int j = 0; j < H; ++j) d.nn.b1[j] = *p++;
+        for (int j = 0; j < H; ++j) d.nn.w2[j] = *p++;
+        d.nn.b2 = *p++;
+    } else {
+        d.nn = NNWeights();
+    }
     return d;
 }
 

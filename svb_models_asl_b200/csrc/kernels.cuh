@@ -15,6 +15,7 @@ struct StepArgs {
     EngineConst ec;
     svbasl_adam ad;
     int32_t update;          // 0: cost + gradient only (svbasl_elbo_grad); 1: fused Adam update (svbasl_step)
+    int32_t n_state;         // rows of state / m / v
     int64_t step;            // iteration index of the first fused iteration (RNG counter / lr_t index)
     float *cost;             // [ld] or NULL
     float *grad;             // [n_state][ld] or NULL
@@ -45,7 +46,6 @@ struct KernelEntry {
     int32_t kind;
     uint32_t flags;          // canonical SVBASL_F_* set
     int32_t nbt;             // compile-time batch size, 0 = any
-    uint32_t mrfmask;
     int32_t n_params;
     step_launcher_t step;
     eval_launcher_t eval;    // only on the nbt == 0, mrfmask == 0 entry
@@ -73,13 +73,42 @@ __device__ __forceinline__ void block_accumulate(float v, double *dst, float *sm
     __syncthreads();
 }
 
-template <class M, int NBT, uint32_t MRFMASK>
-__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ StepArgs a) {
+// 4-byte asynchronous global->shared copy (LDGSTS): the data lands in shared memory without passing through
+// a register, so a load issued before the sample loop costs nothing while the loop runs.
+__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Fused iteration.  Dynamic shared memory: [2][n_state][kBlock] floats when updating (the Adam moments of this
+// CTA's voxels, prefetched asynchronously at kernel start and consumed after the sample loop), else unused.
+// Resident CTAs per SM the register allocation is tuned for: 4 (<= 128 registers) for the common layouts,
+// fewer for the wide posteriors (P' >= 6: the Cholesky factor and its gradient alone are P'(P'+1) registers).
+template <class M>
+constexpr int min_blocks() {
+    return M::kRegHeavy ? 3 : (M::P + 1 <= 5 ? 4 : (M::P + 1 <= 7 ? 3 : 2));
+}
+
+template <class M, int NBT>
+__global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __grid_constant__ StepArgs a) {
+    extern __shared__ float mv_tile[];
     __shared__ float red[kBlock / 32];
+    typedef VoxelStep<M, NBT> VS;
     const int64_t local = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool live = local < a.e.n_vox;
     const int64_t w = a.e.w_begin + (live ? local : 0);
-    VoxelStep<M, NBT, MRFMASK> vs;
+    const int n_state = a.n_state;
+    float *m_sm = mv_tile + threadIdx.x;
+    float *v_sm = mv_tile + (size_t)n_state * kBlock + threadIdx.x;
+    if (a.update) {
+        const float *mg = a.ad.m + w, *vg = a.ad.v + w;
+        for (int k = 0; k < n_state; ++k) {
+            cp_async4(m_sm + k * kBlock, mg + (int64_t)k * a.e.ld);
+            cp_async4(v_sm + k * kBlock, vg + (int64_t)k * a.e.ld);
+        }
+    }
+    VS vs;
     vs.load(a.e, w);
     const int n_iters = a.update ? a.ad.n_iters : 1;
     int skipped = 0;
@@ -87,12 +116,15 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ St
         const int64_t step = a.step + it;
         const int row0 = (a.update && a.ad.n_batches > 1) ? (int)(step % a.ad.n_batches) : a.e.t_row0;
         float cost = vs.elbo_grad(a.md, a.e, a.ec, w, step, row0);
+        if (a.update && it == 0) cp_async_wait_all();          // only this thread reads what it copied: no barrier
         if (live) {
             if (a.cost) a.cost[w] = cost;
             if (a.grad) vs.store_grads(a.e, a.grad, w);
             if (a.update) {
                 if (vs.grads_finite() && cost == cost) {
-                    vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, it == n_iters - 1);
+                    // iteration 0 reads the prefetched moments, later fused iterations re-read global memory
+                    if (it == 0) vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, it == n_iters - 1, m_sm, v_sm, kBlock);
+                    else vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, it == n_iters - 1, a.ad.m + w, a.ad.v + w, a.e.ld);
                 } else {
                     ++skipped;
                     if (it == n_iters - 1) vs.store_state(a.e, w);
@@ -103,13 +135,35 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ St
             cost = 0.0f;
         }
         if (a.cost_sum) block_accumulate(cost, a.cost_sum + it, red);
-        if (MRFMASK != 0 && a.e.ak_grad) {
+        if (a.e.ak_grad) {
 #pragma unroll
-            for (int k = 0; k < VoxelStep<M, NBT, MRFMASK>::NSP; ++k)
-                block_accumulate(live ? vs.ak_out[k] : 0.0f, a.e.ak_grad + k, red);
+            for (int i = 0; i < VS::N; ++i)
+                if (a.e.prior_type[i] == SVBASL_PRIOR_MRF)
+                    block_accumulate(live ? vs.ak_out[i] : 0.0f, a.e.ak_grad + a.ec.sp_slot[i], red);
         }
     }
     if (a.nan_count && skipped) atomicAdd((unsigned long long *)a.nan_count, (unsigned long long)skipped);
+}
+
+// Pre-pass for spatial priors: theta samples of every spatially-regularised parameter, all local voxels
+struct SpatialArgs {
+    svbasl_engine e;
+    EngineConst ec;
+    int64_t n_local;
+    int64_t step;
+    float *out;              // [n_spatial][S][ld]
+};
+
+static __global__ void __launch_bounds__(kBlock) spatial_sample_kernel(const __grid_constant__ SpatialArgs a) {
+    const int64_t u = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (u >= a.n_local) return;
+    const uint32_t key = rng_key(a.e.seed, a.step);
+    for (int p = 0; p < a.e.n_par; ++p) {
+        const int slot = a.ec.sp_slot[p];
+        if (slot < 0) continue;
+        for (int s = 0; s < a.e.n_samples; ++s)
+            a.out[((int64_t)slot * a.e.n_samples + s) * a.e.ld + u] = sample_theta(a.e, key, u, p, s);
+    }
 }
 
 // Model.evaluate: one thread per (row, time point) element of the reference's [W,S,B] output
@@ -152,12 +206,23 @@ __global__ void __launch_bounds__(kBlock) fit_kernel(const __grid_constant__ Fit
 }
 
 inline int check_launch(const char *what);
+void set_error(const char *fmt, ...);
 
-template <class M, int NBT, uint32_t MRFMASK>
+template <class M, int NBT>
 int launch_step(const StepArgs &a, cudaStream_t st) {
     const unsigned grid = (unsigned)((a.e.n_vox + kBlock - 1) / kBlock);
     if (grid == 0) return 0;
-    step_kernel<M, NBT, MRFMASK><<<grid, kBlock, 0, st>>>(a);
+    const size_t smem = a.update ? sizeof(float) * 2 * (size_t)a.n_state * kBlock : 0;
+    static size_t smem_allowed = 48 * 1024;                    // per instantiation
+    if (smem > smem_allowed) {
+        cudaError_t err = cudaFuncSetAttribute(step_kernel<M, NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) {
+            set_error("step_kernel: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(err));
+            return SVBASL_E_CUDA;
+        }
+        smem_allowed = smem;
+    }
+    step_kernel<M, NBT><<<grid, kBlock, smem, st>>>(a);
     return check_launch("step_kernel");
 }
 

@@ -63,6 +63,7 @@ struct AslRest {
     static constexpr int I_FBLOOD = ART ? N_A : -1;
     static constexpr int I_DELTBLOOD = (ART && ATT) ? N_A + 1 : -1;
     static constexpr int P = N_A + (ART ? (1 + (ATT ? 1 : 0)) : 0);
+    static constexpr bool kRegHeavy = false;
     static constexpr int PA = P > 0 ? P : 1;
 
     static constexpr int xf(int) { return SVBASL_XF_IDENTITY; }   // all Normal (aslrest.py:184-246)

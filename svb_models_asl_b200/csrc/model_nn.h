@@ -1,0 +1,95 @@
+// model_nn.h - the aslnn surrogate: signal = ftiss * MLP([t, delttiss]), MLP = 2 -> 10 tanh -> 10 tanh -> 1,
+// with the forward-mode derivative wrt delttiss carried through the network (what TF autodiff produces for
+// /root/reference/svb_models_asl/aslnn.py:93-126, 229-260).  ftiss is LogNormal and delttiss FoldedNormal
+// (aslnn.py:73-81), so the engine feeds exp(theta) and |theta|.
+//
+// SIMT variant: the 151 weights travel in the kernel arguments, i.e. the constant bank, so every FFMA of the
+// 10x10 layer reads its weight as an immediate constant operand - no shared-memory or register traffic for them.
+// Per element: ~280 FFMA/FMUL + 20 tanh (each MUFU.EX2 + MUFU.RCP): FP32 and XU pipes are about equally loaded.
+#pragma once
+#include "compat.h"
+#include "dev_model.h"
+
+namespace svb {
+
+struct AslNN {
+    static constexpr int P = 2;
+    static constexpr bool kRegHeavy = true;
+    static constexpr int PA = 2;
+    static constexpr int H = SVBASL_NN_HIDDEN;
+
+    static constexpr int xf(int p) { return p == 0 ? SVBASL_XF_EXP : SVBASL_XF_ABS; }
+
+    struct Vox {};
+    struct Sample {
+        float f;
+        float a1[H];      // W0[1][j]*delt + b0[j]
+    };
+
+    static SVB_HD Vox load_vox(const DevModel &, int64_t) { return Vox(); }
+
+    static SVB_HD Sample prep_sample(const DevModel &m, const Vox &, const float *x) {
+        Sample s;
+        s.f = x[0];
+        const NNWeights &w = m.nn;
+#pragma unroll
+        for (int j = 0; j < H; ++j) s.a1[j] = w.w0[1][j] * x[1] + w.b0[j];
+        return s;
+    }
+
+    static SVB_HD void eval(const DevModel &m, const Sample &s, float t, float &pred, float *d) {
+        const NNWeights &w = m.nn;
+        float h1[H], dh1[H];
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const float h = ftanh(w.w0[0][j] * t + s.a1[j]);
+            h1[j] = h;
+            dh1[j] = (1.0f - h * h) * w.w0[1][j];
+        }
+        float out = w.b2, dout = 0.0f;
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            float z = w.b1[k], dz = 0.0f;
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                z += w.w1[j][k] * h1[j];
+                dz += w.w1[j][k] * dh1[j];
+            }
+            const float h = ftanh(z);
+            out += w.w2[k] * h;
+            dout += w.w2[k] * (1.0f - h * h) * dz;
+        }
+        pred = s.f * out;
+        d[0] = out;
+        d[1] = s.f * dout;
+    }
+
+    static SVB_HD float predict(const DevModel &m, const Vox &v, const float *x, float t) {
+        Sample s = prep_sample(m, v, x);
+        float pred, d[PA];
+        eval(m, s, t, pred, d);
+        return pred;
+    }
+
+    template <class Acc>
+    static SVB_HD void run(const DevModel &m, const Vox &v, const float *x, Acc &acc) {
+        Sample s = prep_sample(m, v, x);
+        if (Acc::NB > 0) {
+#pragma unroll
+            for (int b = 0; b < (Acc::NB > 0 ? Acc::NB : 1); ++b) {
+                float pred, d[PA];
+                eval(m, s, acc.time(b), pred, d);
+                acc.add(b, pred, d);
+            }
+        } else {
+            const int nb = acc.n();
+            for (int b = 0; b < nb; ++b) {
+                float pred, d[PA];
+                eval(m, s, acc.time(b), pred, d);
+                acc.add(b, pred, d);
+            }
+        }
+    }
+};
+
+}  // namespace svb

@@ -19,6 +19,29 @@ namespace svb {
 SVB_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }       // lower triangle incl. diagonal
 SVB_HD constexpr int stri(int i, int j) { return i * (i - 1) / 2 + j; }      // strict lower triangle (state order)
 
+// Engine-level constants folded on the host (no divisions / logs per voxel)
+struct EngineConst {
+    float pinv[SVBASL_MAX_PAR];     // 1 / prior variance
+    float plog[SVBASL_MAX_PAR];     // log prior variance
+    float t_full, scale, inv_s;     // T, T/B, 1/S
+    int32_t sp_slot[SVBASL_MAX_PAR];// index of parameter i among the spatial ("M") parameters, or -1
+};
+
+inline EngineConst make_engine_const(const svbasl_engine &e) {
+    EngineConst c;
+    int n_sp = 0;
+    for (int i = 0; i < SVBASL_MAX_PAR; ++i) {
+        const bool ok = i < e.n_par && e.prior_var[i] > 0.0f;
+        c.pinv[i] = ok ? 1.0f / e.prior_var[i] : 0.0f;
+        c.plog[i] = ok ? logf(e.prior_var[i]) : 0.0f;
+        c.sp_slot[i] = (i < e.n_par && e.prior_type[i] == SVBASL_PRIOR_MRF) ? n_sp++ : -1;
+    }
+    c.t_full = (float)e.t_full;
+    c.scale = (float)e.t_full / (float)e.n_batch;
+    c.inv_s = 1.0f / (float)e.n_samples;
+    return c;
+}
+
 // Residual accumulator handed to Model::run(): keeps the batch's data/time points in registers (NBT > 0)
 // or re-reads them through L1 (NBT == 0, any batch size).
 template <int P, int NBT>
@@ -67,40 +90,32 @@ struct BatchAcc {
     }
 };
 
-// Engine-level constants folded on the host (no divisions / logs per voxel)
-struct EngineConst {
-    float pinv[SVBASL_MAX_PAR];     // 1 / prior variance
-    float plog[SVBASL_MAX_PAR];     // log prior variance
-    float t_full, scale, inv_s;     // T, T/B, 1/S
-};
-
-inline EngineConst make_engine_const(const svbasl_engine &e) {
-    EngineConst c;
-    for (int i = 0; i < SVBASL_MAX_PAR; ++i) {
-        const bool ok = i < e.n_par && e.prior_var[i] > 0.0f;
-        c.pinv[i] = ok ? 1.0f / e.prior_var[i] : 0.0f;
-        c.plog[i] = ok ? logf(e.prior_var[i]) : 0.0f;
+// One posterior sample theta_p (internal value) of voxel u for sample s: the quantity the spatial prior
+// compares between neighbours.  Written by the pre-pass (kernels.cuh: spatial_sample_kernel) into
+// e.spatial_samples so that the main kernel reads its neighbours' samples instead of rebuilding them.
+// n = P' (runtime here: the pre-pass is model independent).
+SVB_HD float sample_theta(const svbasl_engine &e, uint32_t key, int64_t u, int p, int s) {
+    const int n = e.n_par;
+    const float *st = e.state + u;
+    float th = st[(int64_t)p * e.ld];
+    for (int k = 0; 2 * k <= p; ++k) {
+        float e0, e1;
+        if (e.eps) {
+            e0 = e.eps[((int64_t)(2 * k) * e.n_samples + s) * e.ld + u];
+            e1 = (2 * k + 1 <= p) ? e.eps[((int64_t)(2 * k + 1) * e.n_samples + s) * e.ld + u] : 0.0f;
+        } else {
+            normal2(key, e.vox_offset + u, s, k, e0, e1);
+        }
+        const int j0 = 2 * k, j1 = 2 * k + 1;
+        th += (j0 == p ? fexp(0.5f * st[(int64_t)(n + p) * e.ld]) : st[(int64_t)(2 * n + stri(p, j0)) * e.ld]) * e0;
+        if (j1 <= p)
+            th += (j1 == p ? fexp(0.5f * st[(int64_t)(n + p) * e.ld]) : st[(int64_t)(2 * n + stri(p, j1)) * e.ld]) * e1;
     }
-    c.t_full = (float)e.t_full;
-    c.scale = (float)e.t_full / (float)e.n_batch;
-    c.inv_s = 1.0f / (float)e.n_samples;
-    return c;
+    return th;
 }
 
-SVB_HD constexpr int popc_below(uint32_t mask, int i) {     // set bits of mask strictly below bit i
-    int n = 0;
-    for (int j = 0; j < i; ++j) n += (mask >> j) & 1u;
-    return n;
-}
-
-// MRFMASK: compile-time set of parameters carrying the spatial ("M") prior (bit i = parameter i); the host
-// checks that engine.prior_type agrees.  Keeps the neighbours' samples in registers with static indices.
-template <class M, int NBT, uint32_t MRFMASK>
+template <class M, int NBT>
 struct VoxelStep {
-    static constexpr bool MRF = MRFMASK != 0;
-    static constexpr int NSP = MRF ? popc_below(MRFMASK, 32) : 1;
-    static constexpr bool is_mrf(int i) { return ((MRFMASK >> i) & 1u) != 0; }
-    static constexpr int sp_of(int i) { return popc_below(MRFMASK, i); }
     static constexpr int P = M::P;
     static constexpr int N = P + 1;                 // noise last
     static constexpr int NL = N * (N - 1) / 2;
@@ -111,17 +126,11 @@ struct VoxelStep {
     float lphi[N];                                  // ARD log phi (only ARD slots used)
     // gradients of grad_scale*cost (filled by elbo_grad)
     float g_mu[N], g_lv[N], g_od[NL > 0 ? NL : 1], g_lphi[N];
-    int n_ard;
-
-    SVB_HD int ard_row(const svbasl_engine &e, int i) const {   // state row of parameter i's log phi
-        int k = 0;
-        for (int j = 0; j < i; ++j) k += (e.prior_type[j] == SVBASL_PRIOR_ARD);
-        return 2 * N + NL + k;
-    }
+    float ak_out[N];                                // share of d(sum cost)/d(log ak) of spatial parameter i
 
     SVB_HD void load(const svbasl_engine &e, int64_t w) {
         const float *s = e.state + w;
-        n_ard = 0;
+        int n_ard = 0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             mu[i] = s[(int64_t)i * e.ld];
@@ -139,29 +148,6 @@ struct VoxelStep {
         }
     }
 
-    // theta_p of neighbour voxel u for the 4 samples of group sg, recomputed from its state and its own
-    // draws (counter-based RNG keyed on the global voxel) or read from the eps array in parity mode.
-    static SVB_HD void neighbour_theta4(const svbasl_engine &e, int64_t step, int64_t u, int p, int sg, float th[4]) {
-        const float *st = e.state + u;
-        const float m = st[(int64_t)p * e.ld];
-        th[0] = th[1] = th[2] = th[3] = m;
-#pragma unroll 1
-        for (int j = 0; j <= p; ++j) {
-            const float l = (j == p) ? fexp(0.5f * st[(int64_t)(N + p) * e.ld])
-                                     : st[(int64_t)(2 * N + stri(p, j)) * e.ld];
-            float n4[4];
-            if (e.eps) {
-                for (int k = 0; k < 4; ++k) {
-                    int s = 4 * sg + k;
-                    n4[k] = s < e.n_samples ? e.eps[((int64_t)j * e.n_samples + s) * e.ld + u] : 0.0f;
-                }
-            } else {
-                normal4(e.seed, step, e.vox_offset + u, j, sg, n4);
-            }
-            for (int k = 0; k < 4; ++k) th[k] += l * n4[k];
-        }
-    }
-
     // Cost of this voxel for one batch, gradients left in g_*.  Returns the un-scaled cost.
     SVB_HD float elbo_grad(const DevModel &md, const svbasl_engine &e, const EngineConst &ec, int64_t w, int64_t step,
                            int row0) {
@@ -170,6 +156,7 @@ struct VoxelStep {
         const float scale = ec.scale;
         const float lw = e.latent_weight;
         const bool numeric = (e.latent == SVBASL_LATENT_NUMERIC);
+        const uint32_t key = rng_key(e.seed, step);
         typename M::Vox vox = M::load_vox(md, w);
         BatchAcc<P, NBT> acc;
         acc.load(e, w, row0);
@@ -193,47 +180,21 @@ struct VoxelStep {
                 phi_live[i] = 0.0f;
             }
         }
-        float a_mu[N], a_L[NT], a_phi[N];
+        // a_hyp[i]: ARD log-phi gradient (ARD parameters) or log-ak gradient share (spatial parameters)
+        float a_mu[N], a_L[NT], a_hyp[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) { a_mu[i] = 0.0f; a_phi[i] = 0.0f; }
+        for (int i = 0; i < N; ++i) { a_mu[i] = 0.0f; a_hyp[i] = 0.0f; }
 #pragma unroll
         for (int k = 0; k < NT; ++k) a_L[k] = 0.0f;
         float cost = 0.0f;
-        float ak_part[SVBASL_MAX_SPATIAL] = {0.0f, 0.0f, 0.0f, 0.0f};
 
-        float eg[N][4];                               // draws of the current group of 4 samples
-        float nth[NSP][MRF ? 6 : 1][4];               // neighbours' samples of the same group
-        int nbr_idx[MRF ? 6 : 1];
-        if (MRF) {
-#pragma unroll
-            for (int nbr = 0; nbr < (MRF ? 6 : 1); ++nbr) nbr_idx[nbr] = e.neighbours[(int64_t)nbr * e.ld + w];
-        }
         for (int s = 0; s < S; ++s) {
-            const int k4 = s & 3;
-            if (MRF && k4 == 0) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    if (is_mrf(i)) {
-#pragma unroll
-                        for (int nbr = 0; nbr < (MRF ? 6 : 1); ++nbr) {
-                            if (nbr_idx[nbr] >= 0)
-                                neighbour_theta4(e, step, nbr_idx[nbr], i, s >> 2, nth[MRF ? sp_of(i) : 0][nbr]);
-                        }
-                    }
-                }
-            }
             float eps[N];
             if (e.eps) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) eps[j] = e.eps[((int64_t)j * S + s) * e.ld + w];
             } else {
-                if (k4 == 0) {
-#pragma unroll
-                    for (int j = 0; j < N; ++j) normal4(e.seed, step, e.vox_offset + w, j, s >> 2, eg[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < N; ++j)
-                    eps[j] = k4 == 0 ? eg[j][0] : (k4 == 1 ? eg[j][1] : (k4 == 2 ? eg[j][2] : eg[j][3]));
+                normal_row<N>(key, e.vox_offset + w, s, eps);
             }
             float th[N];
 #pragma unroll
@@ -265,31 +226,32 @@ struct VoxelStep {
             if (numeric) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
-                    if (MRF && is_mrf(i)) {
-                        // -E_s[ 1/2 log ak - ak/4 sum_u (x_w - x_u)^2 ]  
-                        const int sp = MRF ? sp_of(i) : 0;
-                        const float lak = e.log_ak[sp];
+                    if (e.prior_type[i] == SVBASL_PRIOR_MRF) {
+                        // -E_s[ 1/2 log ak - ak/4 sum_u (x_w - x_u)^2 ]  (SURVEY Appendix A.5); the neighbours'
+                        // samples come from the pre-pass buffer [slot][S][ld]
+                        const int slot = ec.sp_slot[i];
+                        const float lak = e.log_ak[slot];
                         const float ak = fexp(lak);
+                        const float *nbs = e.spatial_samples + ((int64_t)slot * S + s) * e.ld;
                         float sdx = 0.0f, sdx2 = 0.0f;
 #pragma unroll
-                        for (int nbr = 0; nbr < (MRF ? 6 : 1); ++nbr) {
-                            if (nbr_idx[nbr] >= 0) {
-                                const float *q4 = nth[sp][nbr];
-                                float tu = k4 == 0 ? q4[0] : (k4 == 1 ? q4[1] : (k4 == 2 ? q4[2] : q4[3]));
-                                float dxu = th[i] - tu;
+                        for (int nbr = 0; nbr < 6; ++nbr) {
+                            const int u = e.neighbours[(int64_t)nbr * e.ld + w];
+                            if (u >= 0) {
+                                const float dxu = th[i] - nbs[u];
                                 sdx += dxu;
                                 sdx2 += dxu * dxu;
                             }
                         }
                         cost += lw * (-0.5f * lak + 0.25f * ak * sdx2);
                         g[i] += lw * ak * sdx;          // own term + the symmetric term of each neighbour's cost
-                        ak_part[sp] += lw * (-0.5f + 0.25f * ak * sdx2);
+                        a_hyp[i] += lw * (-0.5f + 0.25f * ak * sdx2);
                     } else {
                         const float dth = th[i] - pm[i];
                         const float zz = dth * pinv[i];
                         g[i] += lw * zz;
                         cost += lw * 0.5f * (plog[i] + dth * zz);
-                        a_phi[i] += lw * 0.5f * (dth * zz - 1.0f);
+                        a_hyp[i] += lw * 0.5f * (dth * zz - 1.0f);
                     }
                 }
             }
@@ -303,10 +265,9 @@ struct VoxelStep {
         const float invS = ec.inv_s;
         cost *= invS;
 #pragma unroll
-        for (int i = 0; i < N; ++i) { a_mu[i] *= invS; a_phi[i] *= invS; }
+        for (int i = 0; i < N; ++i) { a_mu[i] *= invS; a_hyp[i] *= invS; }
 #pragma unroll
         for (int k = 0; k < NT; ++k) a_L[k] *= invS;
-        for (int k = 0; k < SVBASL_MAX_SPATIAL; ++k) ak_part[k] *= invS;
 
         if (numeric) {
             // entropy term -1/2 log det(cov) = -sum_i log L_ii
@@ -340,7 +301,7 @@ struct VoxelStep {
                 kl += cii * pinv[i] + dm * dm * pinv[i] - 1.0f + plog[i] - lv[i];
                 a_mu[i] += lw * dm * pinv[i];
                 a_L[tri(i, i)] -= lw * frcp(sd[i]);
-                a_phi[i] = lw * 0.5f * (pinv[i] * (cii + dm * dm) - 1.0f);
+                a_hyp[i] = lw * 0.5f * (pinv[i] * (cii + dm * dm) - 1.0f);
             }
             cost += lw * 0.5f * kl;
         }
@@ -349,15 +310,13 @@ struct VoxelStep {
         for (int i = 0; i < N; ++i) {
             g_mu[i] = gs * a_mu[i];
             g_lv[i] = gs * a_L[tri(i, i)] * 0.5f * sd[i];
-            g_lphi[i] = gs * a_phi[i] * phi_live[i];
+            g_lphi[i] = gs * a_hyp[i] * phi_live[i];
+            ak_out[i] = a_hyp[i];
 #pragma unroll
             for (int j = 0; j < i; ++j) g_od[stri(i, j)] = gs * a_L[tri(i, j)];
         }
-        for (int k = 0; k < SVBASL_MAX_SPATIAL; ++k) ak_out[k] = ak_part[k];
         return cost;
     }
-
-    float ak_out[SVBASL_MAX_SPATIAL];   // this voxel's share of d(sum cost)/d(log ak_k)
 
     SVB_HD bool grads_finite() const {
         float acc = 0.0f;
@@ -383,46 +342,47 @@ struct VoxelStep {
             if (e.prior_type[i] == SVBASL_PRIOR_ARD) g[(int64_t)(2 * N + NL + a++) * e.ld] = g_lphi[i];
     }
 
-    static SVB_HD float adam1(const svbasl_adam &ad, float lr_t, float x, float g, float *m, float *v) {
-        float mm = ad.beta1 * (*m) + (1.0f - ad.beta1) * g;
-        float vv = ad.beta2 * (*v) + (1.0f - ad.beta2) * g * g;
-        *m = mm;
-        *v = vv;
-        return x - lr_t * fdiv(mm, fsqrt(vv) + ad.epsilon);
+    static SVB_HD float adam1(const svbasl_adam &ad, float lr_t, float x, float g, float &m, float &v) {
+        m = ad.beta1 * m + (1.0f - ad.beta1) * g;
+        v = ad.beta2 * v + (1.0f - ad.beta2) * g * g;
+        return x - lr_t * fdiv(m, fsqrt(v) + ad.epsilon);
     }
 
-    // tf.train.AdamOptimizer step on this voxel's rows; moments streamed through global memory.
-    // With write_state the new state is stored too (always, unless iterations are being fused).
-    SVB_HD void adam_update(const svbasl_engine &e, const svbasl_adam &ad, float lr_t, int64_t w, bool write_state) {
+    // tf.train.AdamOptimizer step on this voxel's rows.  The old moments are read from (m_rd, v_rd) with row
+    // stride rd_stride - global memory, or the shared-memory tile the kernel prefetched them into - and the
+    // new ones written to global memory.  With write_state the new state is stored too.
+    SVB_HD void adam_update(const svbasl_engine &e, const svbasl_adam &ad, float lr_t, int64_t w, bool write_state,
+                            const float *m_rd, const float *v_rd, int64_t rd_stride) {
         float *m = ad.m + w, *v = ad.v + w, *s = (e.state_out ? e.state_out : e.state) + w;
         int a = 0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
+            float mm = m_rd[(int64_t)i * rd_stride], vv = v_rd[(int64_t)i * rd_stride];
+            mu[i] = adam1(ad, lr_t, mu[i], g_mu[i], mm, vv);
             int64_t o = (int64_t)i * e.ld;
-            float mm = m[o], vv = v[o];
-            mu[i] = adam1(ad, lr_t, mu[i], g_mu[i], &mm, &vv);
             m[o] = mm; v[o] = vv;
             if (write_state) s[o] = mu[i];
+            mm = m_rd[(int64_t)(N + i) * rd_stride]; vv = v_rd[(int64_t)(N + i) * rd_stride];
+            lv[i] = adam1(ad, lr_t, lv[i], g_lv[i], mm, vv);
             o = (int64_t)(N + i) * e.ld;
-            mm = m[o]; vv = v[o];
-            lv[i] = adam1(ad, lr_t, lv[i], g_lv[i], &mm, &vv);
             m[o] = mm; v[o] = vv;
             if (write_state) s[o] = lv[i];
         }
 #pragma unroll
         for (int k = 0; k < NL; ++k) {
-            int64_t o = (int64_t)(2 * N + k) * e.ld;
-            float mm = m[o], vv = v[o];
-            od[k] = adam1(ad, lr_t, od[k], g_od[k], &mm, &vv);
+            float mm = m_rd[(int64_t)(2 * N + k) * rd_stride], vv = v_rd[(int64_t)(2 * N + k) * rd_stride];
+            od[k] = adam1(ad, lr_t, od[k], g_od[k], mm, vv);
+            const int64_t o = (int64_t)(2 * N + k) * e.ld;
             m[o] = mm; v[o] = vv;
             if (write_state) s[o] = od[k];
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             if (e.prior_type[i] == SVBASL_PRIOR_ARD) {
-                int64_t o = (int64_t)(2 * N + NL + a++) * e.ld;
-                float mm = m[o], vv = v[o];
-                lphi[i] = adam1(ad, lr_t, lphi[i], g_lphi[i], &mm, &vv);
+                const int row = 2 * N + NL + a++;
+                float mm = m_rd[(int64_t)row * rd_stride], vv = v_rd[(int64_t)row * rd_stride];
+                lphi[i] = adam1(ad, lr_t, lphi[i], g_lphi[i], mm, vv);
+                const int64_t o = (int64_t)row * e.ld;
                 m[o] = mm; v[o] = vv;
                 if (write_state) s[o] = lphi[i];
             }

@@ -136,8 +136,9 @@ class FusedSvb:
             self.log_ak = torch.full((len(self.mrf),), math.log(ak_init), device=self.dev, dtype=torch.float32)
             self.ak_m, self.ak_v = z(len(self.mrf)), z(len(self.mrf))
             self.ak_grad = z(L.MAX_SPATIAL, dt=torch.float64)
+            self.sp_samples = z(len(self.mrf), self.S, self.ld)
         else:
-            self.log_ak = self.ak_grad = None
+            self.log_ak = self.ak_grad = self.sp_samples = None
         self.eps = None
 
     # ---- descriptors ----
@@ -164,6 +165,7 @@ class FusedSvb:
         e.eps = self.eps.data_ptr() if self.eps is not None else None
         e.seed = self.seed
         e.neighbours = self.neighbours.data_ptr() if self.neighbours is not None else None
+        e.spatial_samples = self.sp_samples.data_ptr() if self.sp_samples is not None else None
         e.log_ak = self.log_ak.data_ptr() if self.log_ak is not None else None
         e.ak_grad = self.ak_grad.data_ptr() if self.ak_grad is not None else None
         return e
@@ -206,6 +208,7 @@ class FusedSvb:
         ad = self.adam_desc(n_iters)
         if self.mrf:
             self.ak_grad.zero_()
+            self.sample_spatial(e, self.step_count)
         cost_ptr = self.cost_hist.data_ptr() + 8 * self.step_count if want_cost else None
         L.check(self.lib.svbasl_step(C.byref(self.mdesc), C.byref(e), C.byref(ad), cost_ptr,
                                      self.nan_count.data_ptr(), _stream_ptr()))
@@ -223,6 +226,10 @@ class FusedSvb:
                                            self.ak_grad.data_ptr(), len(self.mrf), 1.0 / self.n_vox_global, lr_t,
                                            self.b1, self.b2, self.adam_eps, _stream_ptr()))
 
+    def sample_spatial(self, e, step):
+        """Pre-pass: theta samples of the spatially regularised parameters for all local voxels (halo included)."""
+        L.check(self.lib.svbasl_sample_spatial(C.byref(e), self.ld, step, self.sp_samples.data_ptr(), _stream_ptr()))
+
     def elbo_grad(self, step=None, row0=0):
         """-> (cost [ld], grad [n_state, ld]) without updating anything."""
         e = self.engine_desc(row0=row0)
@@ -231,6 +238,7 @@ class FusedSvb:
         grad = torch.zeros(self.n_state, self.ld, device=self.dev)
         if self.mrf:
             self.ak_grad.zero_()
+            self.sample_spatial(e, self.step_count if step is None else step)
         L.check(self.lib.svbasl_elbo_grad(C.byref(self.mdesc), C.byref(e), self.step_count if step is None else step,
                                           cost.data_ptr(), grad.data_ptr(), None, _stream_ptr()))
         return cost, grad

@@ -1,7 +1,8 @@
 """The three `svb.models` entry points of the reference (setup.py:89-95), backed by libsvbasl.so."""
+from .aslnn import AslNNModel  # noqa: F401
 from .aslrest import AslRestModel  # noqa: F401
 
-MODELS = {"aslrest": AslRestModel}
+MODELS = {"aslrest": AslRestModel, "aslnn": AslNNModel}
 
 
 def get_model_class(name):

@@ -54,6 +54,8 @@ class Backend:
             self.lib.hostsim_fill_eps.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                                   C.c_uint64, C.c_int64]
             self.lib.hostsim_fill_eps.restype = None
+            self.lib.hostsim_sample_spatial.argtypes = [C.POINTER(L.Engine), C.c_int64, C.c_int64, C.c_void_p]
+            self.lib.hostsim_sample_spatial.restype = None
 
     # ---- buffers ----
     def put(self, arr, dtype=np.float32):
@@ -87,6 +89,16 @@ class Backend:
     # ---- descriptors ----
     def model_desc(self, cfg, n_vox=None):
         m = L.Model()
+        if isinstance(cfg, dict):                       # aslnn: {"weights": [...], "biases": [...]}
+            m.kind = L.MODEL_ASLNN
+            parts = []
+            for w, b in zip(cfg["weights"], cfg["biases"]):
+                parts += [np.asarray(w, np.float32).reshape(-1), np.asarray(b, np.float32).reshape(-1)]
+            packed = np.ascontiguousarray(np.concatenate(parts))
+            assert packed.size == 151
+            self.keep.append(packed)
+            m.nn_weights = packed.ctypes.data
+            return m
         m.kind = L.MODEL_ASLREST
         m.flags = cfg_flags(cfg)
         m.tau, m.t1b = cfg.tau, cfg.t1b
@@ -157,6 +169,7 @@ class Backend:
         bufs["nbr"] = self.put(neighbours, np.int32) if neighbours is not None else None
         bufs["log_ak"] = self.put(log_ak) if log_ak is not None else None
         bufs["ak_grad"] = self.zeros((4,), np.float64) if log_ak is not None else None
+        bufs["sp"] = self.zeros((len(log_ak), spec.n_samples, ld)) if log_ak is not None else None
         bufs["state_out"] = self.put(state) if state_out else None
         e.state = self.ptr(bufs["state"])
         e.state_out = self.ptr(bufs["state_out"])
@@ -168,9 +181,18 @@ class Backend:
         e.eps = self.ptr(bufs["eps"])
         e.seed = seed
         e.neighbours = self.ptr(bufs["nbr"])
+        e.spatial_samples = self.ptr(bufs["sp"])
         e.log_ak = self.ptr(bufs["log_ak"])
         e.ak_grad = self.ptr(bufs["ak_grad"])
         return e, bufs
+
+    def sample_spatial(self, e, bufs, step=0):
+        """Pre-pass of a step with spatial priors: fills bufs["sp"] (svbasl_sample_spatial)."""
+        if self.kind == "cuda":
+            L.check(self.lib.svbasl_sample_spatial(C.byref(e), e.ld, step, self.ptr(bufs["sp"]), None))
+        else:
+            self.lib.hostsim_sample_spatial(C.byref(e), e.ld, step, self.ptr(bufs["sp"]))
+        return self.get(bufs["sp"])
 
     def elbo_grad(self, m, e, n_state, step=0, nbt=0):
         cost = self.zeros((e.ld,))
@@ -247,6 +269,14 @@ def aslrest_spec(cfg, *, n_samples=10, t_full=6, latent="numeric", cov="LtL", ar
     pm.append(0.0); pv.append(math.log(2e5)); pt.append("N")          # noise: LogNormal(1, 2e5) (Appendix B)
     return eng.EngineSpec("aslrest", cfg, xf=[0] * len(names) + [1], prior_type=pt, prior_mean=pm, prior_var=pv,
                           n_samples=n_samples, t_full=t_full, latent=latent, cov=cov)
+
+
+def nn_spec(weights, biases, *, n_samples=10, t_full=6, latent="numeric", att=1.3):
+    """EngineSpec for aslnn: ftiss LogNormal(1.5; prior var 1e6), delttiss FoldedNormal(att, 1) (aslnn.py:73-81)."""
+    cfg = {"weights": weights, "biases": biases}
+    return eng.EngineSpec("aslnn", cfg, xf=[1, 2, 1], prior_type=["N", "N", "N"],
+                          prior_mean=[math.log(1.5), att, 0.0], prior_var=[math.log(1e6), 1.0, math.log(2e5)],
+                          n_samples=n_samples, t_full=t_full, latent=latent)
 
 
 def synth_problem(cfg, spec, W, rng, *, repeats=1, noise_sd=1.0, slicedt=0.0452, random_state=True):

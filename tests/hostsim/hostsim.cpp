@@ -7,11 +7,12 @@
 
 #include "voxel_step.h"
 #include "model_aslrest.h"
+#include "model_nn.h"
 #include "model_list.h"
 
 using namespace svb;
 
-template <class M, int NBT, uint32_t MRFMASK>
+template <class M, int NBT>
 static int run_step(const svbasl_model *md, const svbasl_engine *e, const svbasl_adam *ad, int64_t step0, float *cost,
                     float *grad, double *cost_sum, double *ak_grad) {
     const int n_iters = ad ? ad->n_iters : 1;
@@ -19,7 +20,7 @@ static int run_step(const svbasl_model *md, const svbasl_engine *e, const svbasl
     const EngineConst ec = make_engine_const(*e);
     for (int64_t local = 0; local < e->n_vox; ++local) {
         const int64_t w = e->w_begin + local;
-        VoxelStep<M, NBT, MRFMASK> vs;
+        VoxelStep<M, NBT> vs;
         vs.load(*e, w);
         for (int it = 0; it < n_iters; ++it) {
             const int64_t step = (ad ? ad->step0 : step0) + it;
@@ -28,12 +29,13 @@ static int run_step(const svbasl_model *md, const svbasl_engine *e, const svbasl
             if (cost) cost[w] = c;
             if (grad) vs.store_grads(*e, grad, w);
             if (ad) {
-                if (vs.grads_finite() && c == c) vs.adam_update(*e, *ad, ad->lr_t[step], w, it == n_iters - 1);
+                if (vs.grads_finite() && c == c) vs.adam_update(*e, *ad, ad->lr_t[step], w, it == n_iters - 1, ad->m + w, ad->v + w, e->ld);
                 else { if (it == n_iters - 1) vs.store_state(*e, w); c = 0.0f; }
             }
             if (cost_sum) cost_sum[it] += c;
-            if (MRFMASK != 0 && ak_grad)
-                for (int k = 0; k < VoxelStep<M, NBT, MRFMASK>::NSP; ++k) ak_grad[k] += vs.ak_out[k];
+            if (ak_grad)
+                for (int i = 0; i < VoxelStep<M, NBT>::N; ++i)
+                    if (e->prior_type[i] == SVBASL_PRIOR_MRF) ak_grad[ec.sp_slot[i]] += vs.ak_out[i];
         }
     }
     return 0;
@@ -61,7 +63,10 @@ static uint32_t canon(uint32_t f) {
     return f;
 }
 
+static bool is_nn(const svbasl_model *md) { return md->kind == SVBASL_MODEL_ASLNN; }
+
 extern "C" int hostsim_n_params(const svbasl_model *md) {
+    if (is_nn(md)) return AslNN::P;
     const uint32_t f = canon(md->flags);
 #define X(F) if (md->kind == SVBASL_MODEL_ASLREST && f == F) return AslRest<F>::P;
     HOSTSIM_ASLREST_FLAGS
@@ -71,6 +76,7 @@ extern "C" int hostsim_n_params(const svbasl_model *md) {
 
 extern "C" int hostsim_evaluate(const svbasl_model *md, const float *params, const float *tpts, float *out,
                                 int64_t n_rows, int n_samples, int n_batch, int64_t n_t_rows) {
+    if (is_nn(md)) return run_eval<AslNN>(md, params, tpts, out, n_rows, n_samples, n_batch, n_t_rows);
     const uint32_t f = canon(md->flags);
 #define X(F) if (md->kind == SVBASL_MODEL_ASLREST && f == F) return run_eval<AslRest<F>>(md, params, tpts, out, n_rows, n_samples, n_batch, n_t_rows);
     HOSTSIM_ASLREST_FLAGS
@@ -81,29 +87,42 @@ extern "C" int hostsim_evaluate(const svbasl_model *md, const float *params, con
 // nbt: 0 = dynamic batch loop, 6 = register-resident batch (only for the fast-path layouts)
 extern "C" int hostsim_step(const svbasl_model *md, const svbasl_engine *e, const svbasl_adam *ad, int64_t step,
                             float *cost, float *grad, double *cost_sum, double *ak_grad, int nbt) {
+    if (is_nn(md)) {
+        if (nbt == 6) return run_step<AslNN, 6>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
+        return run_step<AslNN, 0>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
+    }
     const uint32_t f = canon(md->flags);
-    uint32_t mask = 0;
-    for (int i = 0; i < e->n_par; ++i) if (e->prior_type[i] == SVBASL_PRIOR_MRF) mask |= 1u << i;
-    if (mask == 0 && nbt == 0) {
-#define X(F) if (md->kind == SVBASL_MODEL_ASLREST && f == F) return run_step<AslRest<F>, 0, 0>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
+    if (nbt == 0) {
+#define X(F) if (md->kind == SVBASL_MODEL_ASLREST && f == F) return run_step<AslRest<F>, 0>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
         HOSTSIM_ASLREST_FLAGS
 #undef X
     }
-#define Y(F, NBT, MASK) if (md->kind == SVBASL_MODEL_ASLREST && f == F && nbt == NBT && mask == MASK) return run_step<AslRest<F>, NBT, MASK>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
+#define Y(F, NBT) if (md->kind == SVBASL_MODEL_ASLREST && f == F && nbt == NBT) return run_step<AslRest<F>, NBT>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
     HOSTSIM_FAST
 #undef Y
     return -2;
 }
 
+extern "C" void hostsim_sample_spatial(const svbasl_engine *e, int64_t n_local, int64_t step, float *out) {
+    const EngineConst ec = make_engine_const(*e);
+    const uint32_t key = rng_key(e->seed, step);
+    for (int64_t u = 0; u < n_local; ++u)
+        for (int p = 0; p < e->n_par; ++p) {
+            if (ec.sp_slot[p] < 0) continue;
+            for (int s = 0; s < e->n_samples; ++s)
+                out[((int64_t)ec.sp_slot[p] * e->n_samples + s) * e->ld + u] = sample_theta(*e, key, u, p, s);
+        }
+}
+
 extern "C" void hostsim_fill_eps(float *eps, int64_t n_vox, int64_t ld, int64_t vox_offset, int n_par, int n_samples,
                                  uint64_t seed, int64_t step) {
-    const int groups = (n_samples + 3) / 4;
+    const uint32_t key = rng_key(seed, step);
     for (int64_t w = 0; w < n_vox; ++w)
-        for (int j = 0; j < n_par; ++j)
-            for (int sg = 0; sg < groups; ++sg) {
-                float n4[4];
-                normal4(seed, step, vox_offset + w, j, sg, n4);
-                for (int k = 0; k < 4; ++k)
-                    if (4 * sg + k < n_samples) eps[((int64_t)j * n_samples + 4 * sg + k) * ld + w] = n4[k];
+        for (int s = 0; s < n_samples; ++s)
+            for (int k = 0; 2 * k < n_par; ++k) {
+                float n0, n1;
+                normal2(key, vox_offset + w, s, k, n0, n1);
+                eps[((int64_t)(2 * k) * n_samples + s) * ld + w] = n0;
+                if (2 * k + 1 < n_par) eps[((int64_t)(2 * k + 1) * n_samples + s) * ld + w] = n1;
             }
 }

@@ -277,6 +277,11 @@ def test_spatial_prior_matches_oracle(be, mrf):
     m = be.model_desc(cfg)
     e, bufs = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], eps, neighbours=nb.T.copy(),
                              log_ak=log_ak)
+    sp = be.sample_spatial(e, bufs)
+    # the pre-pass reproduces theta = mu + L eps of the oracle for the spatial parameters
+    _o = H.oracle_cost_grad(spec, prob, eps, hyper=log_ak.astype(np.float64), neighbours=nb, grad_scale=1.0 / W)[3]
+    for slot, p in enumerate(mrf):
+        np.testing.assert_allclose(sp[slot], _o["theta"][:, p, :].detach().numpy().T, rtol=1e-5, atol=1e-5)
     cost, grad, _ = be.elbo_grad(m, e, spec.n_state, nbt=6)
     _check_grads(cost, grad, ocost, ograd)
     ak_grad = be.get(bufs["ak_grad"])[:len(mrf)] / W
@@ -314,3 +319,42 @@ def test_in_kernel_rng_equals_memory_eps(be):
     c2, g2, _ = be.elbo_grad(m, e2, spec.n_state, step=17, nbt=6)
     np.testing.assert_allclose(c1, c2, rtol=1e-5)
     assert H.rel_err(g2, g1).max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# aslnn surrogate
+def _nn_weights(golden):
+    n = golden("aslnn_eval")["nn"]
+    return n, [n["w%i" % i] for i in range(3)], [n["b%i" % i] for i in range(3)]
+
+
+def test_nn_evaluate_matches_reference_golden(be, golden):
+    """AslNNModel.evaluate (aslnn.py:93-126) on the golden inputs of the reference source."""
+    n, ws, bs = _nn_weights(golden)
+    out = be.evaluate({"weights": ws, "biases": bs}, n["params"], n["t"], n["params"].shape[2])
+    ref = n["out64"]
+    assert np.abs(out - ref).max() <= FWD_TOL * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("latent", ["numeric", "analytic"])
+@pytest.mark.parametrize("nbt", [0, 6])
+def test_nn_elbo_grad_matches_oracle(be, golden, latent, nbt):
+    """LogNormal / FoldedNormal transforms + MLP forward-mode derivative against autograd."""
+    _n, ws, bs = _nn_weights(golden)
+    rng = np.random.default_rng(21)
+    W = 64
+    spec = H.nn_spec(ws, bs, latent=latent)
+    tpts = np.repeat(np.asarray(H.TIS, dtype=np.float32)[:, None], W, 1)
+    state = np.stack([rng.normal(1.5, 0.5, W), rng.normal(1.2, 0.6, W) * rng.choice([-1, 1], W), rng.normal(0, 0.3, W)]
+                     + [rng.normal(-2, 0.5, W) for _ in range(3)] + [rng.normal(0, 0.05, W) for _ in range(3)])
+    state = state.astype(np.float32).astype(np.float64)
+    f = torch.as_tensor(np.exp(state[0])).reshape(W, 1, 1)
+    d = torch.as_tensor(np.abs(state[1])).reshape(W, 1, 1)
+    clean = om.evaluate_nn(ws, bs, f, d, torch.as_tensor(tpts.astype(np.float64)).T.unsqueeze(1))[:, 0, :].T.numpy()
+    prob = {"state": state, "tpts": tpts, "data": (clean + rng.normal(0, 0.5, clean.shape)).astype(np.float32)}
+    eps = rng.normal(size=(3, spec.n_samples, W)).astype(np.float32)
+    ocost, ograd, _gh, _ = H.oracle_cost_grad(spec, prob, eps)
+    m = be.model_desc(spec.cfg)
+    e, _b = be.engine_desc(spec, state, prob["data"], tpts, eps)
+    cost, grad, _ = be.elbo_grad(m, e, spec.n_state, nbt=nbt)
+    _check_grads(cost, grad, ocost, ograd)
