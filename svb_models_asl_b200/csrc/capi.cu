@@ -27,6 +27,9 @@ static uint32_t canonical_flags(const svbasl_model *m) {
         if (f & SVBASL_F_ARTONLY) f |= SVBASL_F_INFERART;                      // aslrest.py:137-138
         if (f & SVBASL_F_INFERWM) f |= SVBASL_F_INCWM;                        // aslrest.py:103-105
         if (f & SVBASL_F_ARTONLY) f &= ~(uint32_t)(SVBASL_F_INCWM | SVBASL_F_INFERWM);
+    } else if (m->kind == SVBASL_MODEL_ASLREST_DISP) {
+        f &= (SVBASL_F_CASL | SVBASL_F_INFERATT | SVBASL_F_INFERART | SVBASL_F_ARTONLY | SVBASL_F_DISP_INFER);
+        if (f & SVBASL_F_ARTONLY) f |= SVBASL_F_INFERART;
     } else if (m->kind == SVBASL_MODEL_ASLNN) {
         f = 0;
     }
@@ -85,6 +88,13 @@ static int validate(const svbasl_model *m, const svbasl_engine *e, const KernelE
     if (e->n_par != k->n_params + 1) {
         set_error("engine n_par=%d but the model has %d parameters (+1 noise)", e->n_par, k->n_params);
         return SVBASL_E_INVALID;
+    }
+    if (m->kind == SVBASL_MODEL_ASLREST_DISP) {
+        if (m->flags & (SVBASL_F_INCWM | SVBASL_F_INFERWM | SVBASL_F_INFERT1)) {
+            set_error("aslrest_disp: WM / T1 inference is not supported with dispersion");
+            return SVBASL_E_UNSUPPORTED;
+        }
+        if (m->conv_nt < 2 || !(m->conv_tmax > 0.0f) || !(m->conv_dt > 0.0f)) { set_error("aslrest_disp: bad convolution grid"); return SVBASL_E_INVALID; }
     }
     if (m->kind == SVBASL_MODEL_ASLNN && !m->nn_weights) { set_error("aslnn needs nn_weights"); return SVBASL_E_INVALID; }
     if (m->kind == SVBASL_MODEL_ASLREST && (canonical_flags(m) & SVBASL_F_INFERT1) == 0 && !(m->t1 > 0.0f)) {

@@ -76,6 +76,7 @@ struct DevModel {
     const float *pvgm, *pvwm;
     float conv_dt, conv_tmax;
     int32_t conv_nt;
+    float conv_h, conv_inv_h, conv_rho;   // grid step of linspace(0,tmax,nt), its inverse, exp(-h/T1app)
     float s_fixed, sp_fixed;
     NNWeights nn;
 };
@@ -106,6 +107,9 @@ inline DevModel make_dev_model(const svbasl_model &m) {
     d.conv_dt = m.conv_dt;
     d.conv_tmax = m.conv_tmax;
     d.conv_nt = m.conv_nt;
+    d.conv_h = m.conv_nt > 1 ? m.conv_tmax / (float)(m.conv_nt - 1) : 0.0f;
+    d.conv_inv_h = d.conv_h > 0.0f ? 1.0f / d.conv_h : 0.0f;
+    d.conv_rho = expf(-d.conv_h * d.gm.q);
     d.s_fixed = m.s_fixed;
     d.sp_fixed = m.sp_fixed;
     if (m.kind == SVBASL_MODEL_ASLNN && m.nn_weights) {

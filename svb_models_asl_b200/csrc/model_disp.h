@@ -1,0 +1,293 @@
+// model_disp.h - ASL kinetic model with gamma-kernel bolus dispersion: AIF(t) with regularised incomplete
+// gamma functions, tissue curve = AIF convolved with the well-mixed residue exp(-t/T1app) on a regular grid,
+// sampled at the time points by linear interpolation; arterial component = fblood * AIF(t).
+//
+// Takes over AslRestDisp (/root/reference/svb_models_asl/aslrest_disp.py): aif_gammadisp :69-110,
+// resid_wellmix :133-146, conv_tf :148-171, the tfp interpolation :63, art_signal :66-67 - and the backward pass
+// TensorFlow builds through tf.math.igammac (including d/da, which has no closed form).
+// Decisions for the defects of the file as shipped: SURVEY.md Appendix C1-C4: the parent's
+// 8-argument call is honoured, the residue is per voxel, pv is applied, and the post-bolus AIF is the intended
+// kc*(Q(k,s(t-d-tau)) - Q(k,s(t-d))) unless SVBASL_F_DISP_ASWRITTEN asks for the shipped `gamma2 - gamma2` == 0.
+//
+// conv_tf is algebraically a causal discrete convolution times dt (golden-checked), and with an exponential
+// residue that is the O(NT) recurrence C[i] = rho*C[i-1] + dt*AIF[i], rho = exp(-h/T1app);
+// value and the derivatives wrt (delt, s, sp) are carried through it in forward mode, one sweep per sample.
+#pragma once
+#include "compat.h"
+#include "dev_model.h"
+
+namespace svb {
+
+struct GammaConst {       // per (voxel, sample): everything about a = k that does not depend on x
+    float a;              // k = 1 + min(sp, 10)
+    float lg_a;           // lgamma(a)
+    float psi_a;          // digamma(a)
+    float ln_a, inv_a;
+};
+
+// digamma for a in (1, 11]: recurrence up to >= 6, then the asymptotic series
+SVB_HD float digamma_f(float a) {
+    float r = 0.0f;
+#pragma unroll 1
+    while (a < 6.0f) {
+        r -= frcp(a);
+        a += 1.0f;
+    }
+    const float i = frcp(a), i2 = i * i;
+    return r + flog(a) - 0.5f * i - i2 * (1.0f / 12.0f - i2 * (1.0f / 120.0f - i2 * (1.0f / 252.0f)));
+}
+
+SVB_HD GammaConst gamma_const(float a) {
+    GammaConst g;
+    g.a = a;
+    g.lg_a = lgammaf(a);
+    g.psi_a = digamma_f(a);
+    g.ln_a = flog(a);
+    g.inv_a = frcp(a);
+    return g;
+}
+
+// Q(a,x) = regularised upper incomplete gamma, with dQ/da and dQ/dx (forward-mode
+// accumulation through the series / modified-Lentz continued fraction).  lnx = log(x).
+SVB_HD void igammac_d(const GammaConst &g, float x, float lnx, float &Q, float &dQa, float &dQx) {
+    const float a = g.a;
+    if (!(x > 0.0f)) {
+        Q = 1.0f; dQa = 0.0f; dQx = 0.0f;                 // a > 1: the density vanishes at 0
+        return;
+    }
+    // density term x^(a-1) e^-x / Gamma(a) (= -dQ/dx) and the common prefactor exp(a ln x - x - lgamma(a))
+    const float pre = fexp(a * lnx - x - g.lg_a);
+    dQx = -pre * frcp(x);
+    if (x < a + 1.0f) {
+        // P = pre/a * sum_n t_n, t_0 = 1, t_n = t_{n-1} x/(a+n);  d t_n/da = -t_n H_n, H_n = sum_{k<=n} 1/(a+k)
+        float t = 1.0f, sum = 1.0f, dsum = 0.0f, h = 0.0f, an = a;
+#pragma unroll 1
+        for (int n = 1; n < 200; ++n) {
+            an += 1.0f;
+            const float ian = frcp(an);
+            t *= x * ian;
+            h += ian;
+            sum += t;
+            dsum -= t * h;
+            if (t < sum * 6e-8f) break;
+        }
+        const float d = pre * g.inv_a;                    // exp(a ln x - x - lgamma(a+1))
+        const float dlog = lnx - (g.psi_a + g.inv_a);     // d log d / da = ln x - psi(a+1)
+        Q = 1.0f - d * sum;
+        dQa = -d * (dlog * sum + dsum);
+    } else {
+        // Q = pre * h, continued fraction b0 = x+1-a, a_i = -i(i-a), b_i = b_{i-1}+2 (modified Lentz),
+        // carrying the a-derivatives of c, d and h
+        const float tiny = 1e-30f;
+        float b = x + 1.0f - a, db = -1.0f;
+        float c = 1.0f / tiny, dc = 0.0f;
+        float d = frcp(b), dd = -db * d * d;
+        float h = d, dh = dd;
+#pragma unroll 1
+        for (int i = 1; i < 200; ++i) {
+            const float fi = (float)i;
+            const float an = -fi * (fi - a), dan = fi;
+            b += 2.0f;
+            float dn = an * d + b;
+            float ddn = dan * d + an * dd + db;
+            if (fabsf(dn) < tiny) dn = tiny;
+            const float ic = frcp(c);
+            float cn = b + an * ic;
+            float dcn = db + (dan - an * dc * ic) * ic;
+            if (fabsf(cn) < tiny) cn = tiny;
+            d = frcp(dn);
+            dd = -ddn * d * d;
+            c = cn;
+            dc = dcn;
+            const float del = d * c;
+            const float ddel = dd * c + d * dc;
+            dh = dh * del + h * ddel;
+            h *= del;
+            if (fabsf(del - 1.0f) < 1.2e-7f) break;
+        }
+        Q = pre * h;
+        dQa = pre * ((lnx - g.psi_a) * h + dh);
+    }
+}
+
+// accumulator for a single time point (forward evaluation through the same sweep)
+struct OnePointAcc {
+    static constexpr int NB = 0;
+    float t, out;
+    SVB_HD int n() const { return 1; }
+    SVB_HD float time(int) const { return t; }
+    SVB_HD void add(int, float pred, const float *) { out = pred; }
+};
+
+template <uint32_t F>
+struct AslDisp {
+    static constexpr bool CASL = (F & SVBASL_F_CASL) != 0;
+    static constexpr bool ATT = (F & SVBASL_F_INFERATT) != 0;
+    static constexpr bool ART = (F & (SVBASL_F_INFERART | SVBASL_F_ARTONLY)) != 0;
+    static constexpr bool ARTONLY = (F & SVBASL_F_ARTONLY) != 0;
+    static constexpr bool TISS = !ARTONLY;
+    static constexpr bool DISP = (F & SVBASL_F_DISP_INFER) != 0;
+
+    // parameter order: aslrest.py:183-246 then s, sp (aslrest_disp.py:32-38)
+    static constexpr int I_FTISS = TISS ? 0 : -1;
+    static constexpr int I_DELT = (TISS && ATT) ? 1 : -1;
+    static constexpr int N_A = TISS ? (1 + (ATT ? 1 : 0)) : 0;
+    static constexpr int I_FBLOOD = ART ? N_A : -1;
+    static constexpr int I_DELTBLOOD = (ART && ATT) ? N_A + 1 : -1;
+    static constexpr int N_B = N_A + (ART ? (1 + (ATT ? 1 : 0)) : 0);
+    static constexpr int I_S = DISP ? N_B : -1;
+    static constexpr int I_SP = DISP ? N_B + 1 : -1;
+    static constexpr int P = N_B + (DISP ? 2 : 0);
+    static constexpr int PA = P > 0 ? P : 1;
+    static constexpr bool kRegHeavy = true;
+
+    static constexpr int xf(int p) { return (DISP && p >= N_B) ? SVBASL_XF_EXP : SVBASL_XF_IDENTITY; }
+    static constexpr int ix(int i) { return i < 0 ? 0 : i; }
+
+    struct Vox {
+        float pvgm;
+    };
+    static SVB_HD Vox load_vox(const DevModel &m, int64_t w) {
+        Vox v;
+        v.pvgm = m.pvgm ? m.pvgm[w] : m.pvgm_s;
+        return v;
+    }
+
+    struct Disp {             // per-sample dispersion terms
+        float s, ln_s;
+        bool sp_live;         // false when sp is clipped at 10 (zero gradient, aslrest_disp.py:85)
+        GammaConst g;
+    };
+
+    static SVB_HD Disp prep_disp(const DevModel &m, const float *x) {
+        Disp d;
+        d.s = DISP ? x[ix(I_S)] : m.s_fixed;
+        const float sp = DISP ? x[ix(I_SP)] : m.sp_fixed;
+        d.sp_live = sp < 10.0f;
+        d.ln_s = flog(d.s);
+        d.g = gamma_const(1.0f + fmin2(sp, 10.0f));
+        return d;
+    }
+
+    // AIF(t; delt) and its derivatives wrt delt, s, sp  (aslrest_disp.py:91-108)
+    static SVB_HD void aif(const DevModel &m, const Disp &dp, float t, float delt, float kc_casl, float &A, float &dAd,
+                           float &dAs, float &dAsp) {
+        A = dAd = dAs = dAsp = 0.0f;
+        const float u = t - delt;
+        if (u < 0.0f) return;                                   // pre-bolus (t < delt)
+        const bool post = t > delt + m.tau;
+        const float kc = CASL ? kc_casl : 2.0f * fexp(-t * m.inv_t1b);
+        const float dkc = CASL ? -kc * m.inv_t1b : 0.0f;
+        float q1, q1a, q1x;
+        igammac_d(dp.g, dp.s * u, dp.ln_s + flog(fmax2(u, 1e-30f)), q1, q1a, q1x);
+        float q2 = 1.0f, q2a = 0.0f, q2x = 0.0f, u2 = 0.0f;
+        if (post) {
+            if (m.flags & SVBASL_F_DISP_ASWRITTEN) return;      // kc*(gamma2 - gamma2) == 0 as shipped
+            u2 = u - m.tau;
+            igammac_d(dp.g, dp.s * u2, dp.ln_s + flog(fmax2(u2, 1e-30f)), q2, q2a, q2x);
+        }
+        // during: kc (1 - g1); post: kc (g2 - g1)
+        const float base = (post ? q2 : 1.0f) - q1;
+        A = kc * base;
+        // d/d delt: x_i = s (t - delt - ...) -> dx/d delt = -s
+        dAd = dkc * base + kc * (-dp.s) * ((post ? q2x : 0.0f) - q1x);
+        dAs = kc * ((post ? q2x * u2 : 0.0f) - q1x * u);
+        dAsp = dp.sp_live ? kc * ((post ? q2a : 0.0f) - q1a) : 0.0f;
+    }
+
+    template <class Acc>
+    static SVB_HD void run(const DevModel &m, const Vox &v, const float *x, Acc &acc) {
+        const Disp dp = prep_disp(m, x);
+        const int nb = acc.n();
+        const float fb = ART ? x[ix(I_FBLOOD)] : 0.0f;
+        const float deltb = (I_DELTBLOOD >= 0) ? x[ix(I_DELTBLOOD)] : m.artt;
+        const float kcb = CASL ? 2.0f * fexp(-deltb * m.inv_t1b) : 0.0f;
+        const float s_chain = DISP ? dp.s : 0.0f;                          // d s / d theta_s = s
+        const float sp_chain = DISP ? x[ix(I_SP)] : 0.0f;
+
+        // arterial part at one time point, added to (pred, d)
+        auto arterial = [&](float t, float &pred, float *d) {
+            if (!ART) return;
+            float A, dAd, dAs, dAsp;
+            aif(m, dp, t, deltb, kcb, A, dAd, dAs, dAsp);
+            pred += fb * A;
+            d[ix(I_FBLOOD)] = A;
+            if (I_DELTBLOOD >= 0) d[ix(I_DELTBLOOD)] = fb * dAd;
+            if (DISP) {
+                d[ix(I_S)] += fb * dAs * s_chain;
+                d[ix(I_SP)] += fb * dAsp * sp_chain;
+            }
+        };
+
+        if (!TISS) {
+            for (int b = 0; b < nb; ++b) {
+                float pred = 0.0f, d[PA];
+#pragma unroll
+                for (int p = 0; p < P; ++p) d[p] = 0.0f;
+                arterial(acc.time(b), pred, d);
+                acc.add(b, pred, d);
+            }
+            return;
+        }
+
+        const float f = x[ix(I_FTISS)];
+        const float delt = ATT ? x[ix(I_DELT)] : m.att;
+        const float kct = CASL ? 2.0f * fexp(-delt * m.inv_t1b) : 0.0f;
+        const float pvf = v.pvgm * f;
+        const int nt = m.conv_nt;
+        const float h = m.conv_h;                 // grid step of linspace(0, tmax, nt)  (aslrest_disp.py:43)
+        const float to_pos = m.conv_inv_h;        // t -> grid position
+        const float rho = m.conv_rho;             // exp(-h/T1app)
+        int last = 0;
+        for (int b = 0; b < nb; ++b) {
+            const float pos = fmin2(fmax2(acc.time(b) * to_pos, 0.0f), (float)(nt - 1));
+            int lo = (int)pos;
+            lo = lo > nt - 2 ? nt - 2 : lo;
+            last = lo + 1 > last ? lo + 1 : last;
+        }
+        float C = 0.0f, Cd = 0.0f, Cs = 0.0f, Csp = 0.0f;
+#pragma unroll 1
+        for (int i = 0; i <= last; ++i) {
+            const float ti = (float)i * h;
+            float A, dAd, dAs, dAsp;
+            aif(m, dp, ti, delt, kct, A, dAd, dAs, dAsp);
+            const float pC = C, pCd = Cd, pCs = Cs, pCsp = Csp;
+            C = rho * C + m.conv_dt * A;
+            Cd = rho * Cd + m.conv_dt * dAd;
+            Cs = rho * Cs + m.conv_dt * dAs;
+            Csp = rho * Csp + m.conv_dt * dAsp;
+            if (i == 0) continue;
+            // emit every time point that falls in [grid[i-1], grid[i]]  (linear interpolation, constant extension)
+            for (int b = 0; b < nb; ++b) {
+                const float t = acc.time(b);
+                const float pos = fmin2(fmax2(t * to_pos, 0.0f), (float)(nt - 1));
+                int lo = (int)pos;
+                lo = lo > nt - 2 ? nt - 2 : lo;
+                if (lo != i - 1) continue;
+                const float fr = pos - (float)lo;
+                const float S = pC + fr * (C - pC);
+                float pred = pvf * S, d[PA];
+#pragma unroll
+                for (int p = 0; p < P; ++p) d[p] = 0.0f;
+                d[ix(I_FTISS)] = v.pvgm * S;
+                if (ATT) d[ix(I_DELT)] = pvf * (pCd + fr * (Cd - pCd));
+                if (DISP) {
+                    d[ix(I_S)] = pvf * (pCs + fr * (Cs - pCs)) * s_chain;
+                    d[ix(I_SP)] = pvf * (pCsp + fr * (Csp - pCsp)) * sp_chain;
+                }
+                arterial(t, pred, d);
+                acc.add(b, pred, d);
+            }
+        }
+    }
+
+    static SVB_HD float predict(const DevModel &m, const Vox &v, const float *x, float t) {
+        OnePointAcc one;
+        one.t = t;
+        one.out = 0.0f;
+        run(m, v, x, one);
+        return one.out;
+    }
+};
+
+}  // namespace svb

@@ -8,6 +8,7 @@
 #include "voxel_step.h"
 #include "model_aslrest.h"
 #include "model_nn.h"
+#include "model_disp.h"
 #include "model_list.h"
 
 using namespace svb;
@@ -64,9 +65,21 @@ static uint32_t canon(uint32_t f) {
 }
 
 static bool is_nn(const svbasl_model *md) { return md->kind == SVBASL_MODEL_ASLNN; }
+static uint32_t canon_disp(uint32_t f) {
+    f &= (SVBASL_F_CASL | SVBASL_F_INFERATT | SVBASL_F_INFERART | SVBASL_F_ARTONLY | SVBASL_F_DISP_INFER);
+    if (f & SVBASL_F_ARTONLY) f |= SVBASL_F_INFERART;
+    return f;
+}
 
 extern "C" int hostsim_n_params(const svbasl_model *md) {
     if (is_nn(md)) return AslNN::P;
+    if (md->kind == SVBASL_MODEL_ASLREST_DISP) {
+        const uint32_t fd = canon_disp(md->flags);
+#define X(F) if (fd == F) return AslDisp<F>::P;
+        HOSTSIM_DISP_FLAGS
+#undef X
+        return -1;
+    }
     const uint32_t f = canon(md->flags);
 #define X(F) if (md->kind == SVBASL_MODEL_ASLREST && f == F) return AslRest<F>::P;
     HOSTSIM_ASLREST_FLAGS
@@ -77,6 +90,13 @@ extern "C" int hostsim_n_params(const svbasl_model *md) {
 extern "C" int hostsim_evaluate(const svbasl_model *md, const float *params, const float *tpts, float *out,
                                 int64_t n_rows, int n_samples, int n_batch, int64_t n_t_rows) {
     if (is_nn(md)) return run_eval<AslNN>(md, params, tpts, out, n_rows, n_samples, n_batch, n_t_rows);
+    if (md->kind == SVBASL_MODEL_ASLREST_DISP) {
+        const uint32_t fd = canon_disp(md->flags);
+#define X(F) if (fd == F) return run_eval<AslDisp<F>>(md, params, tpts, out, n_rows, n_samples, n_batch, n_t_rows);
+        HOSTSIM_DISP_FLAGS
+#undef X
+        return -2;
+    }
     const uint32_t f = canon(md->flags);
 #define X(F) if (md->kind == SVBASL_MODEL_ASLREST && f == F) return run_eval<AslRest<F>>(md, params, tpts, out, n_rows, n_samples, n_batch, n_t_rows);
     HOSTSIM_ASLREST_FLAGS
@@ -90,6 +110,13 @@ extern "C" int hostsim_step(const svbasl_model *md, const svbasl_engine *e, cons
     if (is_nn(md)) {
         if (nbt == 6) return run_step<AslNN, 6>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
         return run_step<AslNN, 0>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
+    }
+    if (md->kind == SVBASL_MODEL_ASLREST_DISP) {
+        const uint32_t fd = canon_disp(md->flags);
+#define X(F) if (fd == F) return run_step<AslDisp<F>, 0>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
+        HOSTSIM_DISP_FLAGS
+#undef X
+        return -2;
     }
     const uint32_t f = canon(md->flags);
     if (nbt == 0) {
