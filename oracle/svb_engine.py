@@ -127,8 +127,12 @@ def voxel_cost(spec, state, hyper, data, t, eps, neighbours=None):
     # materialise every operand at the full [W,S,B] shape, as TF's tile/broadcast kernels do (and because
     # torch's CPU broadcasting of [W,S,1] x [W,1,B] operands is ~50x slower than dense element-wise ops)
     full = (state.shape[1], S, B)
-    ext = [transform(spec.xf[p], theta[:, p, :]).unsqueeze(-1).expand(full).contiguous() for p in range(n - 1)]
-    pred = model_predict(spec, ext, t.T.unsqueeze(1).expand(full).contiguous())   # [W,S,B]
+    if getattr(spec.cfg, "disp", False):      # the dispersion model works on its own [W,S,NT] grid
+        ext = [transform(spec.xf[p], theta[:, p, :]).unsqueeze(-1) for p in range(n - 1)]
+        pred = model_predict(spec, ext, t.T.unsqueeze(1).contiguous())
+    else:
+        ext = [transform(spec.xf[p], theta[:, p, :]).unsqueeze(-1).expand(full).contiguous() for p in range(n - 1)]
+        pred = model_predict(spec, ext, t.T.unsqueeze(1).expand(full).contiguous())   # [W,S,B]
     log_nv = theta[:, n - 1, :]                                     # noise is LogNormal: var = exp(theta_n)
     nv = torch.exp(log_nv)
     ssd = torch.square(data.T.unsqueeze(1).expand(full).contiguous() - pred).sum(-1)          # [W,S]

@@ -6,6 +6,7 @@ this package on a machine without a GPU works (descriptors, option handling, I/O
 from .plugin import MODELS, get_model_class  # noqa: F401
 from .plugin.aslrest import AslRestModel  # noqa: F401
 from .plugin.aslnn import AslNNModel  # noqa: F401
+from .plugin.aslrest_disp import AslRestDisp  # noqa: F401
 
 __version__ = "0.1.0+b200"
-__all__ = ["AslRestModel", "AslNNModel", "MODELS", "get_model_class", "__version__"]
+__all__ = ["AslRestModel", "AslRestDisp", "AslNNModel", "MODELS", "get_model_class", "__version__"]

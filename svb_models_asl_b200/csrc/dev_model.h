@@ -70,7 +70,7 @@ struct DevModel {
     float tau, half_tau, inv_t1b;
     float att, attwm, fwm, artt;
     float fc_pc, fc_pc_wm;            // fcalib/pc
-    float leadscale, inv_leadscale;
+    float leadscale, inv_leadscale, inv_leadscale_s;   // _s: times sqrt(log2 e)
     TissueRates gm, wm;               // for the fixed t1 / t1wm of the options
     float pvgm_s, pvwm_s;
     const float *pvgm, *pvwm;
@@ -97,6 +97,7 @@ inline DevModel make_dev_model(const svbasl_model &m) {
     d.fc_pc_wm = m.pcwm != 0.0f ? m.fcalibwm / m.pcwm : 0.0f;
     d.leadscale = m.leadscale;
     d.inv_leadscale = m.leadscale != 0.0f ? 1.0f / m.leadscale : 0.0f;
+    d.inv_leadscale_s = d.inv_leadscale * 1.2011224087864498f;
     const bool casl = (m.flags & SVBASL_F_CASL) != 0;
     d.gm = tissue_rates((m.t1 > 0.0f ? 1.0f / m.t1 : 0.0f) + d.fc_pc, m.tau, d.inv_t1b, casl);
     d.wm = tissue_rates((m.t1wm > 0.0f ? 1.0f / m.t1wm : 0.0f) + d.fc_pc_wm, m.tau, d.inv_t1b, casl);

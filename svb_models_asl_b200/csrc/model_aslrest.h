@@ -18,19 +18,22 @@ namespace svb {
 
 // 1/2 (1 + erf z) and exp(-z^2)/sqrt(pi) together, branch-free, from ONE exponential:
 // erfc(|z|) = (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p|z|)  (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7),
-// so the smoothed step is accurate to 7.5e-8 absolute - below float32 resolution of values near 1.  |z| is
-// clamped at 8 (erfc(8) ~ 1e-29) to keep exp(-z^2) a normal number.
-SVB_HD void erf_step(float z, float &half_1p_erf, float &gauss) {
-    const float a = fmin2(fabsf(z), 8.0f);
-    const float t = frcp(1.0f + 0.3275911f * a);
-    float p = 1.061405429f;
-    p = p * t - 1.453152027f;
-    p = p * t + 1.421413741f;
-    p = p * t - 0.284496736f;
-    p = p * t + 0.254829592f;
-    const float g0 = fexp(-a * a);
-    const float half_erfc = 0.5f * p * t * g0;
-    half_1p_erf = z >= 0.0f ? 1.0f - half_erfc : half_erfc;
+// so the smoothed step is accurate to 7.5e-8 absolute - below float32 resolution of values near 1.
+// The argument arrives pre-scaled, zs = z*sqrt(log2 e), so that exp(-z^2) = 2^(-zs^2) is one FMUL + MUFU.EX2;
+// |zs| is clamped at 9.6 (|z| = 8, erfc ~ 1e-29) to keep the exponential a normal number.  The polynomial
+// coefficients carry the factor 1/2 of the half-step.
+#define SVB_SQRT_LOG2E 1.2011224087864498f
+SVB_HD void erf_step_scaled(float zs, float &half_1p_erf, float &gauss) {
+    const float a = fmin2(fabsf(zs), 9.6f);
+    const float t = frcp(1.0f + (0.3275911f / SVB_SQRT_LOG2E) * a);
+    float p = 0.5f * 1.061405429f;
+    p = p * t - 0.5f * 1.453152027f;
+    p = p * t + 0.5f * 1.421413741f;
+    p = p * t - 0.5f * 0.284496736f;
+    p = p * t + 0.5f * 0.254829592f;
+    const float g0 = fexp2(-a * a);
+    const float half_erfc = (p * t) * g0;
+    half_1p_erf = zs >= 0.0f ? 1.0f - half_erfc : half_erfc;
     gauss = 0.5641895835477563f * g0;
 }
 
@@ -81,7 +84,7 @@ struct AslRest {
     struct Sample {
         Tissue gm, wm;
         float fb, deltb, kc, dkc;                     // arterial (aslrest.py:404-407)
-        float thr_out, inv_ls, dz_in_c, dz_in_t;     // lead-in/out (aslrest.py:411-419)
+        float thr_out, inv_ls_s, dz_in_c, dz_in_t;   // lead-in/out (aslrest.py:411-419); _s: x sqrt(log2 e)
         bool leadin_ok;
     };
 
@@ -135,7 +138,7 @@ struct AslRest {
             // tf.minimum routes the gradient to deltblood when it is the smaller argument: z_in = t/db - 1
             const bool own = db <= m.leadscale;
             const float ils = own ? frcp(s.leadin_ok ? ls : 1.0f) : m.inv_leadscale;
-            s.inv_ls = ils;
+            s.inv_ls_s = ils * SVB_SQRT_LOG2E;
             s.dz_in_c = own ? 0.0f : -ils;
             s.dz_in_t = own ? -ils * ils : 0.0f;
         }
@@ -209,10 +212,11 @@ struct AslRest {
             const bool leadout = t > s.thr_out;                             // aslrest.py:411
             const bool active = leadout || s.leadin_ok;                     // aslrest.py:419
             const float u = t - s.deltb;
-            const float z = leadout ? -(u - m.tau) * m.inv_leadscale : u * s.inv_ls;   // aslrest.py:422-423
+            // z of aslrest.py:422-423, scaled by sqrt(log2 e) for erf_step_scaled
+            const float zs = leadout ? (m.tau - u) * m.inv_leadscale_s : u * s.inv_ls_s;
             const float dz = leadout ? m.inv_leadscale : (s.dz_in_c + s.dz_in_t * t);
             float h, g;
-            erf_step(z, h, g);
+            erf_step_scaled(zs, h, g);
             const float A = active ? kc * h : 0.0f;
             const float dA = active ? (dkc * h + kc * g * dz) : 0.0f;
             pred += s.fb * A;

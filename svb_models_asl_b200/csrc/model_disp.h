@@ -202,8 +202,8 @@ struct AslDisp {
         const float fb = ART ? x[ix(I_FBLOOD)] : 0.0f;
         const float deltb = (I_DELTBLOOD >= 0) ? x[ix(I_DELTBLOOD)] : m.artt;
         const float kcb = CASL ? 2.0f * fexp(-deltb * m.inv_t1b) : 0.0f;
-        const float s_chain = DISP ? dp.s : 0.0f;                          // d s / d theta_s = s
-        const float sp_chain = DISP ? x[ix(I_SP)] : 0.0f;
+        // derivatives are with respect to the model-space values (s, sp); the LogNormal chain factor
+        // d exp(theta)/d theta is applied by the engine (voxel_step.h)
 
         // arterial part at one time point, added to (pred, d)
         auto arterial = [&](float t, float &pred, float *d) {
@@ -214,8 +214,8 @@ struct AslDisp {
             d[ix(I_FBLOOD)] = A;
             if (I_DELTBLOOD >= 0) d[ix(I_DELTBLOOD)] = fb * dAd;
             if (DISP) {
-                d[ix(I_S)] += fb * dAs * s_chain;
-                d[ix(I_SP)] += fb * dAsp * sp_chain;
+                d[ix(I_S)] += fb * dAs;
+                d[ix(I_SP)] += fb * dAsp;
             }
         };
 
@@ -272,8 +272,8 @@ struct AslDisp {
                 d[ix(I_FTISS)] = v.pvgm * S;
                 if (ATT) d[ix(I_DELT)] = pvf * (pCd + fr * (Cd - pCd));
                 if (DISP) {
-                    d[ix(I_S)] = pvf * (pCs + fr * (Cs - pCs)) * s_chain;
-                    d[ix(I_SP)] = pvf * (pCsp + fr * (Csp - pCsp)) * sp_chain;
+                    d[ix(I_S)] = pvf * (pCs + fr * (Cs - pCs));
+                    d[ix(I_SP)] = pvf * (pCsp + fr * (Csp - pCsp));
                 }
                 arterial(t, pred, d);
                 acc.add(b, pred, d);

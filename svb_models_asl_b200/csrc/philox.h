@@ -16,9 +16,9 @@ SVB_HD void philox2x32_10(uint32_t c0, uint32_t c1, uint32_t key, uint32_t &o0, 
     const uint32_t M = 0xD256D193u, W = 0x9E3779B9u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi = mulhi32(M, c0), lo = M * c0;
-        c0 = hi ^ key ^ c1;
-        c1 = lo;
+        const uint64_t prod = (uint64_t)M * (uint64_t)c0;     // one IMAD.WIDE.U32
+        c0 = (uint32_t)(prod >> 32) ^ key ^ c1;
+        c1 = (uint32_t)prod;
         key += W;
     }
     o0 = c0;

@@ -180,6 +180,9 @@ struct VoxelStep {
                 phi_live[i] = 0.0f;
             }
         }
+        float lw_pinv[N];                              // latent_weight / prior variance
+#pragma unroll
+        for (int i = 0; i < N; ++i) lw_pinv[i] = lw * pinv[i];
         // a_hyp[i]: ARD log-phi gradient (ARD parameters) or log-ak gradient share (spatial parameters)
         float a_mu[N], a_L[NT], a_hyp[N];
 #pragma unroll
@@ -247,11 +250,12 @@ struct VoxelStep {
                         g[i] += lw * ak * sdx;          // own term + the symmetric term of each neighbour's cost
                         a_hyp[i] += lw * (-0.5f + 0.25f * ak * sdx2);
                     } else {
+                        // -log N(theta; m, v) up to the constant 1/2 log v (added once after the loop);
+                        // a_hyp accumulates lw*(theta-m)^2/v, which is also the ARD log-phi gradient term
                         const float dth = th[i] - pm[i];
-                        const float zz = dth * pinv[i];
-                        g[i] += lw * zz;
-                        cost += lw * 0.5f * (plog[i] + dth * zz);
-                        a_hyp[i] += lw * 0.5f * (dth * zz - 1.0f);
+                        const float zz = dth * lw_pinv[i];
+                        g[i] += zz;
+                        a_hyp[i] += dth * zz;
                     }
                 }
             }
@@ -263,6 +267,16 @@ struct VoxelStep {
             }
         }
         const float invS = ec.inv_s;
+        if (numeric) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                if (e.prior_type[i] != SVBASL_PRIOR_MRF) {
+                    const float q = a_hyp[i];                           // sum_s lw (theta-m)^2 / v
+                    cost += 0.5f * q + (float)S * lw * 0.5f * plog[i];
+                    a_hyp[i] = 0.5f * (q - (float)S * lw);              // sum_s lw/2 ((theta-m)^2/v - 1)
+                }
+            }
+        }
         cost *= invS;
 #pragma unroll
         for (int i = 0; i < N; ++i) { a_mu[i] *= invS; a_hyp[i] *= invS; }

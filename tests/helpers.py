@@ -99,8 +99,14 @@ class Backend:
             self.keep.append(packed)
             m.nn_weights = packed.ctypes.data
             return m
-        m.kind = L.MODEL_ASLREST
+        m.kind = L.MODEL_ASLREST_DISP if cfg.disp else L.MODEL_ASLREST
         m.flags = cfg_flags(cfg)
+        if cfg.disp:
+            m.flags |= (L.F_DISP_INFER if cfg.infer_disp_params else 0)
+            m.flags |= (L.F_DISP_ASWRITTEN if cfg.disp_postbolus == "as_written" else 0)
+            m.conv_dt, m.conv_tmax = cfg.conv_dt, cfg.conv_tmax
+            m.conv_nt = 1 + int(cfg.conv_tmax / cfg.conv_dt)
+            m.s_fixed, m.sp_fixed = cfg.s_fixed, cfg.sp_fixed
         m.tau, m.t1b = cfg.tau, cfg.t1b
         m.t1, m.pc, m.fcalib, m.att = (float(np.mean(x)) for x in (cfg.t1, cfg.pc, cfg.fcalib, cfg.att))
         m.t1wm, m.pcwm, m.fcalibwm, m.attwm, m.fwm = (float(np.mean(x)) for x in
@@ -262,12 +268,17 @@ def aslrest_spec(cfg, *, n_samples=10, t_full=6, latent="numeric", cov="LtL", ar
             pm.append(0.0); pv.append(1e6); pt.append("A" if ard else "N")
         elif n == "deltblood":
             pm.append(cfg.artt); pv.append(1.0); pt.append("N")
+        elif n == "s":                                                 # LogNormal(7.4, 2) geometric
+            pm.append(math.log(7.4)); pv.append(math.log(2.0)); pt.append("N")
+        elif n == "sp":
+            pm.append(math.log(0.74)); pv.append(math.log(2.0)); pt.append("N")
         else:
             raise KeyError(n)
     for i in mrf:
         pt[i] = "M"
     pm.append(0.0); pv.append(math.log(2e5)); pt.append("N")          # noise: LogNormal(1, 2e5) (Appendix B)
-    return eng.EngineSpec("aslrest", cfg, xf=[0] * len(names) + [1], prior_type=pt, prior_mean=pm, prior_var=pv,
+    xf = [1 if n in ("s", "sp") else 0 for n in names] + [1]
+    return eng.EngineSpec("aslrest", cfg, xf=xf, prior_type=pt, prior_mean=pm, prior_var=pv,
                           n_samples=n_samples, t_full=t_full, latent=latent, cov=cov)
 
 
@@ -295,6 +306,10 @@ def synth_problem(cfg, spec, W, rng, *, repeats=1, noise_sd=1.0, slicedt=0.0452,
             truth[n] = rng.uniform(0, 10, W) * (rng.uniform(size=W) < 0.3)
         elif n == "deltblood":
             truth[n] = np.maximum(truth.get("delttiss", rng.uniform(0.6, 2.5, W)) - 0.3, 0.05)
+        elif n == "s":
+            truth[n] = rng.uniform(3.0, 12.0, W)
+        elif n == "sp":
+            truth[n] = rng.uniform(0.3, 2.0, W)
     z = rng.integers(0, 24, W)
     tis = np.repeat(np.asarray(TIS), repeats)
     tpts = (tis[:, None] + (z * slicedt)[None, :]).astype(np.float32)          # [T,W]
@@ -305,7 +320,10 @@ def synth_problem(cfg, spec, W, rng, *, repeats=1, noise_sd=1.0, slicedt=0.0452,
     if random_state:
         rows = []
         for i, nme in enumerate(names):
-            rows.append(truth[nme] + rng.normal(0, 0.3, W))
+            if nme in ("s", "sp"):                                             # internal value is the log
+                rows.append(np.log(truth[nme]) + rng.normal(0, 0.2, W))
+            else:
+                rows.append(truth[nme] + rng.normal(0, 0.3, W))
         rows.append(rng.normal(0.3, 0.3, W))                                   # log noise variance
         for i in range(n):                                                     # log variances
             tight = i < len(names) and names[i] in ("t1", "t1wm")              # keep sampled T1 well away from 0

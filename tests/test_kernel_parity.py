@@ -358,3 +358,79 @@ def test_nn_elbo_grad_matches_oracle(be, golden, latent, nbt):
     e, _b = be.engine_desc(spec, state, prob["data"], tpts, eps)
     cost, grad, _ = be.elbo_grad(m, e, spec.n_state, nbt=nbt)
     _check_grads(cost, grad, ocost, ograd)
+
+
+# ------------------------------------------------------------------------------------------------
+# aslrest_disp: gamma-dispersed AIF, convolution recurrence, interpolation
+DISP_CASES = {
+    "casl_tiss": dict(casl=True),
+    "casl_tiss_art": dict(casl=True, inferart=True),
+    "pasl_tiss_art": dict(casl=False, inferart=True),
+    "casl_artonly": dict(casl=True, artonly=True),
+    "casl_fixed_disp": dict(casl=True, inferart=True, infer_disp_params=False),
+    "casl_as_written": dict(casl=True, inferart=True, disp_postbolus="as_written"),
+    "casl_noatt": dict(casl=True, inferart=True, inferatt=False),
+}
+
+
+def _disp_cfg(case):
+    return om.AslConfig(tau=1.8, t1b=1.65, disp=True, **DISP_CASES[case])
+
+
+def test_disp_aif_and_convolution_match_reference_pieces(be, golden):
+    """The reference's own building blocks (aslrest_disp.py:69-110,133-171,63; goldens run on its source):
+    arterial-only evaluation == fblood * aif_gammadisp(t) in the as-written form, and the tissue curve from the
+    kernel's recurrence + interpolation == tfp-interp(conv_tf(aif, resid))."""
+    d = golden("disp_pieces")["disp"]
+    W, S = d["delt"].shape[:2]
+    t = d["t"].astype(np.float32)                                           # [W,1,B]
+    # arterial only, as written: params fblood=1, deltblood=delt, s, sp
+    cfg = om.AslConfig(casl=True, artonly=True, disp=True, disp_postbolus="as_written", tau=1.8, t1b=1.65)
+    params = np.stack([np.ones_like(d["delt"]), d["delt"], d["s"], d["sp"]]).astype(np.float32)
+    out = be.evaluate(cfg, params, t, S)
+    ref = d["aif_at_t_as_written"]
+    assert np.abs(out - ref).max() <= FWD_TOL * np.abs(ref).max()
+    # tissue only, as written (matches conv_tf + interpolation of the shipped AIF): ftiss=1
+    cfg_t = om.AslConfig(casl=True, disp=True, disp_postbolus="as_written", tau=1.8, t1b=1.65)
+    params_t = np.stack([np.ones_like(d["delt"]), d["delt"], d["s"], d["sp"]]).astype(np.float32)
+    out_t = be.evaluate(cfg_t, params_t, t, S)
+    ref_t = d["interp"]
+    assert np.abs(out_t - ref_t).max() <= 2 * FWD_TOL * np.abs(ref_t).max()
+
+
+@pytest.mark.parametrize("case", sorted(DISP_CASES))
+def test_disp_evaluate_matches_oracle(be, case):
+    cfg = _disp_cfg(case)
+    rng = np.random.default_rng(zlib.crc32(case.encode()))
+    W, S = 24, 2
+    names = cfg.param_names()
+    cols = []
+    for n in names:
+        lo, hi = {"ftiss": (1, 20), "delttiss": (0.3, 2.4), "fblood": (0, 10), "deltblood": (0.2, 2.0),
+                  "s": (1.5, 25.0), "sp": (0.05, 12.0)}[n]
+        cols.append(rng.uniform(lo, hi, (W, S, 1)))
+    params = np.stack(cols).astype(np.float32)
+    z = rng.integers(0, 24, W)
+    t = (np.asarray(H.TIS)[None, :] + (z * 0.0452)[:, None]).astype(np.float32).reshape(W, 1, -1)
+    out = be.evaluate(cfg, params, t, S)
+    ref = om.evaluate(cfg, [torch.as_tensor(p, dtype=torch.float64) for p in params],
+                      torch.as_tensor(t, dtype=torch.float64)).numpy()
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref).max() <= 3 * FWD_TOL * np.abs(ref).max(), np.abs(out - ref).max() / np.abs(ref).max()
+
+
+@pytest.mark.parametrize("case", ["casl_tiss", "casl_tiss_art", "pasl_tiss_art", "casl_fixed_disp"])
+def test_disp_elbo_grad_matches_oracle(be, case):
+    """Gradient through Q(a,x) (incl. dQ/da), the recurrence and the interpolation vs the oracle
+    (autograd with fp64 finite differences of scipy's gammaincc for dQ/da)."""
+    cfg = _disp_cfg(case)
+    rng = np.random.default_rng(zlib.crc32(case.encode()) + 1)
+    W = 32
+    spec = H.aslrest_spec(cfg, n_samples=4)
+    prob = H.synth_problem(cfg, spec, W, rng, noise_sd=0.5)
+    eps = rng.normal(size=(spec.n_par, spec.n_samples, W)).astype(np.float32)
+    ocost, ograd, _gh, _ = H.oracle_cost_grad(spec, prob, eps)
+    m = be.model_desc(cfg)
+    e, _b = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], eps)
+    cost, grad, _ = be.elbo_grad(m, e, spec.n_state)
+    _check_grads(cost, grad, ocost, ograd, tol=3 * GRAD_TOL)
