@@ -140,6 +140,10 @@ class FusedSvb:
         else:
             self.log_ak = self.ak_grad = self.sp_samples = None
         self.eps = None
+        # multi-GPU hooks (svb_models_asl_b200/sharding.py): halo_exchange(state) refreshes the halo columns from
+        # the adjacent ranks; reduce_fn(tensor) sums a small tensor over all ranks in place
+        self.halo_exchange = None
+        self.reduce_fn = None
 
     # ---- descriptors ----
     def engine_desc(self, row0=0):
@@ -214,7 +218,9 @@ class FusedSvb:
                                      self.nan_count.data_ptr(), _stream_ptr()))
         if self.mrf:
             self.state, self.state_alt = self.state_alt, self.state
-            self._hyper_step()
+            self._hyper_step(self.reduce_fn)
+            if self.halo_exchange is not None:
+                self.halo_exchange(self.state)
         self.step_count += n_iters
         return self.cost_hist[self.step_count - n_iters:self.step_count]
 

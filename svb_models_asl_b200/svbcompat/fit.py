@@ -19,6 +19,7 @@ from . import dist as _dist
 from .parameter import Parameter
 from .utils import LogBase
 from ..ops import FusedSvb, device_array
+from ..sharding import ShardPlan, shard_bounds, world_info
 
 
 def noise_parameter():
@@ -30,18 +31,7 @@ def noise_parameter():
     return Parameter("noise", prior=_dist.LogNormal(1.0, 2e5), post=_dist.LogNormal(1.0, 1.02), post_init=_init)
 
 
-def _dist_world():
-    import torch.distributed as td
-    if td.is_available() and td.is_initialized():
-        return td.get_rank(), td.get_world_size()
-    return 0, 1
-
-
-def shard_bounds(n, rank, world):
-    """Contiguous voxel range of `rank`: voxel order is x-slowest, so these are x-slabs."""
-    base, rem = divmod(n, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+_dist_world = world_info
 
 
 class SvbFit(LogBase):
@@ -72,13 +62,19 @@ class SvbFit(LogBase):
         prior_types = [p.prior_type for p in self.params]
         neighbours = None
         halo = (0, 0)
+        self.plan = ShardPlan(self.data_model.n_nodes, self.rank, self.world,
+                              self.data_model.neighbour_table() if "M" in prior_types else None)
+        if (self.lo, self.hi) != (self.plan.lo, self.plan.hi):           # caller overrode the shard (bench.py)
+            self.plan = ShardPlan(hi - lo, 0, 1, None)
+            self.plan.lo, self.plan.hi = lo, hi
+        plan = self.plan
         if "M" in prior_types:
-            if self.world > 1:
-                raise NotImplementedError("spatial priors across GPUs: use svb_models_asl_b200.spatial.ShardedSpatialFit")
-            neighbours = self.data_model.neighbour_table().T.copy()      # [6, W] local == global indices
+            neighbours = plan.neighbours_local                           # [6, ld], local indices
+            halo = (plan.halo_lo, plan.halo_hi)
+        g0, g1 = lo - halo[0], hi + halo[1]                              # local arrays cover [g0, g1) of the global order
         n_batches = int(math.ceil(n_t / (batch_size or n_t)))
         self.fused = FusedSvb(
-            self.model, data[lo:hi].T.copy(), tpts[lo:hi].T.copy(), n_samples=sample_size,
+            self.model, data[g0:g1].T.copy(), tpts[g0:g1].T.copy(), n_samples=sample_size,
             batch_size=batch_size or n_t, latent=latent, cov_llt=(kwargs.get("cov_convention", "LtL") == "LLt"),
             learning_rate=learning_rate, seed=int(kwargs.get("seed", 1)), prior_types=prior_types,
             prior_means=[np.mean(p.prior_dist.mean) for p in self.params],
@@ -101,6 +97,10 @@ class SvbFit(LogBase):
             means.append(np.asarray(mean, dtype=np.float32)[lo:hi])
             variances.append(np.asarray(var, dtype=np.float32)[lo:hi])
         self.fused.set_posterior(means, variances)
+        if self.world > 1 and "M" in prior_types:
+            self.fused.halo_exchange = plan.exchange_halo
+            self.fused.reduce_fn = ShardPlan.allreduce_sum
+            plan.exchange_halo(self.fused.state)
 
     # ------------------------------------------------------------------
     def train(self, tpts, data, batch_size=None, epochs=100, learning_rate=0.1, sample_size=None, display_step=1,
