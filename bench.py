@@ -124,7 +124,7 @@ def cpu_port_rate(n_vox, n_iters, seed=20260101, threads=None):
     return n_vox / sec, sec, threads
 
 
-def run_reference(args):
+def run_reference(args, out):
     """--impl reference: the reference's CPU path (oracle port) on the host cores, same metric/config."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -143,11 +143,21 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "voxel-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 # ----------------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """Library chatter (e.g. NCCL's version banner) goes to stderr; stdout carries exactly ONE JSON line."""
+    real = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -159,7 +169,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import torch
     import torch.distributed as td
@@ -294,7 +304,8 @@ def main():
         line["cpu_baseline"] = {"value": rate, "unit": "voxel-iters/s", "cores": threads, "kind": "port",
                                 "sample": "%d voxels x %d iterations (%.1f s/iter); PyTorch-CPU op-for-op port of the "
                                           "reference TF graph" % (args.cpu_voxels, args.cpu_iters, sec)}
-    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + "\n")
+    out.flush()
     if world > 1:
         td.destroy_process_group()
 

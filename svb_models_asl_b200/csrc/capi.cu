@@ -36,9 +36,12 @@ static uint32_t canonical_flags(const svbasl_model *m) {
     return f;
 }
 
-static const KernelEntry *find_entry(const svbasl_model *m, int nbt, bool want_eval) {
+// Best kernel for (model layout, batch size): prefers the compile-time batch size, and the lean (production)
+// flavour when the call allows it.
+static const KernelEntry *find_entry(const svbasl_model *m, int nbt, bool want_eval, bool lean_ok = false) {
     const uint32_t f = canonical_flags(m);
-    const KernelEntry *fallback = nullptr;
+    const KernelEntry *best = nullptr;
+    int best_score = -1;
     for (int g = 0; g < kNumEntryGroups; ++g) {
         for (const KernelEntry *e = kEntryGroups[g](); e->kind >= 0; ++e) {
             if (e->kind != m->kind || e->flags != f) continue;
@@ -46,11 +49,13 @@ static const KernelEntry *find_entry(const svbasl_model *m, int nbt, bool want_e
                 if (e->eval) return e;
                 continue;
             }
-            if (e->nbt == nbt) return e;
-            if (e->nbt == 0) fallback = e;
+            if (e->nbt != nbt && e->nbt != 0) continue;
+            if (e->lean && !lean_ok) continue;
+            const int score = (e->nbt == nbt ? 2 : 0) + (e->lean ? 1 : 0);
+            if (score > best_score) { best = e; best_score = score; }
         }
     }
-    return fallback;
+    return best;
 }
 
 static uint32_t mrf_mask(const svbasl_engine *e) {
@@ -60,7 +65,7 @@ static uint32_t mrf_mask(const svbasl_engine *e) {
     return mask;
 }
 
-static int validate(const svbasl_model *m, const svbasl_engine *e, const KernelEntry **entry) {
+static int validate(const svbasl_model *m, const svbasl_engine *e, const KernelEntry **entry, bool lean_ok) {
     if (!m || !e) { set_error("null descriptor"); return SVBASL_E_INVALID; }
     if (e->n_vox < 0 || e->w_begin < 0 || e->ld < e->w_begin + e->n_vox) {
         set_error("bad extents: n_vox=%lld w_begin=%lld ld=%lld", (long long)e->n_vox, (long long)e->w_begin, (long long)e->ld);
@@ -80,7 +85,8 @@ static int validate(const svbasl_model *m, const svbasl_engine *e, const KernelE
         set_error("spatial prior without neighbours / log_ak / spatial_samples (call svbasl_sample_spatial first)");
         return SVBASL_E_INVALID;
     }
-    const KernelEntry *k = find_entry(m, e->n_batch, false);
+    const KernelEntry *k = find_entry(m, e->n_batch, false,
+                                      lean_ok && !mask && !e->eps && e->latent == SVBASL_LATENT_NUMERIC);
     if (!k) {
         set_error("no kernel compiled for model kind=%d flags=0x%x", m->kind, canonical_flags(m));
         return SVBASL_E_UNSUPPORTED;
@@ -233,7 +239,7 @@ int svbasl_evaluate(const svbasl_model *model, const float *params, const float 
 static int run_step(const svbasl_model *model, const svbasl_engine *engine, const svbasl_adam *adam, int64_t step,
                     float *cost, float *grad, double *cost_sum, long long *nan_count, void *stream) {
     const KernelEntry *k = nullptr;
-    int rc = validate(model, engine, &k);
+    int rc = validate(model, engine, &k, adam != nullptr && !cost && !grad);
     if (rc) return rc;
     StepArgs a;
     memset(&a, 0, sizeof(a));

@@ -46,6 +46,7 @@ struct KernelEntry {
     int32_t kind;
     uint32_t flags;          // canonical SVBASL_F_* set
     int32_t nbt;             // compile-time batch size, 0 = any
+    int32_t lean;            // 1: production flavour (update, Philox, numeric latent loss, no spatial prior, no outputs)
     int32_t n_params;
     step_launcher_t step;
     eval_launcher_t eval;    // only on the nbt == 0, mrfmask == 0 entry
@@ -90,18 +91,20 @@ constexpr int min_blocks() {
     return M::kRegHeavy ? 3 : (M::P + 1 <= 5 ? 4 : (M::P + 1 <= 7 ? 3 : 2));
 }
 
-template <class M, int NBT>
+// LEAN = production flavour: fused update, no per-voxel cost / gradient outputs (see VoxelStep)
+template <class M, int NBT, bool LEAN>
 __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ float mv_tile[];
     __shared__ float red[kBlock / 32];
-    typedef VoxelStep<M, NBT> VS;
+    typedef VoxelStep<M, NBT, LEAN> VS;
+    const bool update = LEAN || a.update;
     const int64_t local = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool live = local < a.e.n_vox;
     const int64_t w = a.e.w_begin + (live ? local : 0);
     const int n_state = a.n_state;
     float *m_sm = mv_tile + threadIdx.x;
     float *v_sm = mv_tile + (size_t)n_state * kBlock + threadIdx.x;
-    if (a.update) {
+    if (update) {
         const float *mg = a.ad.m + w, *vg = a.ad.v + w;
         for (int k = 0; k < n_state; ++k) {
             cp_async4(m_sm + k * kBlock, mg + (int64_t)k * a.e.ld);
@@ -110,17 +113,17 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
     }
     VS vs;
     vs.load(a.e, w);
-    const int n_iters = a.update ? a.ad.n_iters : 1;
+    const int n_iters = update ? a.ad.n_iters : 1;
     int skipped = 0;
     for (int it = 0; it < n_iters; ++it) {
         const int64_t step = a.step + it;
-        const int row0 = (a.update && a.ad.n_batches > 1) ? (int)(step % a.ad.n_batches) : a.e.t_row0;
+        const int row0 = (update && a.ad.n_batches > 1) ? (int)(step % a.ad.n_batches) : a.e.t_row0;
         float cost = vs.elbo_grad(a.md, a.e, a.ec, w, step, row0);
-        if (a.update && it == 0) cp_async_wait_all();          // only this thread reads what it copied: no barrier
+        if (update && it == 0) cp_async_wait_all();          // only this thread reads what it copied: no barrier
         if (live) {
-            if (a.cost) a.cost[w] = cost;
-            if (a.grad) vs.store_grads(a.e, a.grad, w);
-            if (a.update) {
+            if (!LEAN && a.cost) a.cost[w] = cost;
+            if (!LEAN && a.grad) vs.store_grads(a.e, a.grad, w);
+            if (update) {
                 if (vs.grads_finite() && cost == cost) {
                     // iteration 0 reads the prefetched moments, later fused iterations re-read global memory
                     if (it == 0) vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, it == n_iters - 1, m_sm, v_sm, kBlock);
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
             cost = 0.0f;
         }
         if (a.cost_sum) block_accumulate(cost, a.cost_sum + it, red);
-        if (a.e.ak_grad) {
+        if (!LEAN && a.e.ak_grad) {
 #pragma unroll
             for (int i = 0; i < VS::N; ++i)
                 if (a.e.prior_type[i] == SVBASL_PRIOR_MRF)
@@ -208,21 +211,21 @@ __global__ void __launch_bounds__(kBlock) fit_kernel(const __grid_constant__ Fit
 inline int check_launch(const char *what);
 void set_error(const char *fmt, ...);
 
-template <class M, int NBT>
+template <class M, int NBT, bool LEAN>
 int launch_step(const StepArgs &a, cudaStream_t st) {
     const unsigned grid = (unsigned)((a.e.n_vox + kBlock - 1) / kBlock);
     if (grid == 0) return 0;
     const size_t smem = a.update ? sizeof(float) * 2 * (size_t)a.n_state * kBlock : 0;
     static size_t smem_allowed = 48 * 1024;                    // per instantiation
     if (smem > smem_allowed) {
-        cudaError_t err = cudaFuncSetAttribute(step_kernel<M, NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t err = cudaFuncSetAttribute(step_kernel<M, NBT, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) {
             set_error("step_kernel: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(err));
             return SVBASL_E_CUDA;
         }
         smem_allowed = smem;
     }
-    step_kernel<M, NBT><<<grid, kBlock, smem, st>>>(a);
+    step_kernel<M, NBT, LEAN><<<grid, kBlock, smem, st>>>(a);
     return check_launch("step_kernel");
 }
 

@@ -67,9 +67,27 @@ struct AslRest {
     static constexpr int xf(int) { return SVBASL_XF_IDENTITY; }   // all Normal (aslrest.py:184-246)
     static constexpr int ix(int i) { return i < 0 ? 0 : i; }
 
+    static constexpr int kMaxNB = 8;
     struct Vox {              // per-voxel constants
         float pvgm, pvwm;
+        // exp(-t_b/T1app) of the batch's time points (register-resident batches with a fixed T1 only): the
+        // per-element exponential exp(-(t_b - delta)/T1app) then factorises into eb[b] * exp(delta/T1app)
+        float eb[kMaxNB], ebw[kMaxNB];
     };
+
+    template <class Acc>
+    static constexpr bool use_eb() { return Acc::NB > 0 && Acc::NB <= kMaxNB && !T1; }
+
+    template <class Acc>
+    static SVB_HD void bind_times(const DevModel &m, Vox &v, const Acc &acc) {
+        if (use_eb<Acc>() && TISS) {
+#pragma unroll
+            for (int b = 0; b < (Acc::NB > 0 && Acc::NB <= kMaxNB ? Acc::NB : 1); ++b) {
+                v.eb[b] = fexp2(acc.time(b) * m.gm.nk);
+                if (INCWM) v.ebw[b] = fexp2(acc.time(b) * m.wm.nk);
+            }
+        }
+    }
 
     // One tissue compartment's per-sample terms.  `k` is a copy of the constant-bank rates when T1 is fixed
     // (the compiler keeps reading the constant bank) and per-sample values when T1 is inferred.
@@ -77,6 +95,7 @@ struct AslRest {
         TissueRates k;
         float delt, tdp;      // delta, fl(tau + delta)             (mask thresholds, aslrest.py:362-363)
         float A;              // CASL: 2*T1app*exp(-delta/t1b) (aslrest.py:371); PASL: 2*exp(r*delta)
+        float AE;             // CASL with eb[]: A * exp(delta/T1app), so that A*E = AE * eb[b]
         float pvf, pv;        // pv*f, pv
         float dqdt1;          // dq/dt1 = -1/t1^2
     };
@@ -111,6 +130,7 @@ struct AslRest {
             ts.dqdt1 = 0.0f;
         }
         ts.A = CASL ? ts.k.two_iq * fexp(-delt * m.inv_t1b) : 2.0f * fexp(ts.k.r * delt);
+        ts.AE = (CASL && !T1_SAMPLED) ? ts.k.two_iq * fexp(delt * (ts.k.q - m.inv_t1b)) : 0.0f;
     }
 
     // x[P]: model-space parameter values for this sample
@@ -146,14 +166,16 @@ struct AslRest {
     }
 
     // value S (per unit pv*f) and derivatives wrt delta and q of one tissue compartment at time t
-    template <bool WANT_Q>
-    static SVB_HD void tissue_eval(const DevModel &m, const Tissue &ts, float t, float &S, float &dSdd, float &dSdq) {
+    // USE_EB: ebt = exp(-t/T1app) is supplied (Vox::eb), saving the per-element exponential
+    template <bool WANT_Q, bool USE_EB>
+    static SVB_HD void tissue_eval(const DevModel &m, const Tissue &ts, float t, float ebt, float &S, float &dSdd,
+                                   float &dSdq) {
         const bool post = t > ts.tdp;
         const bool during = (t > ts.delt) && !post;
         const float u = t - ts.delt;
         if (CASL) {
-            const float E = fexp2(u * ts.k.nk);            // exp(-(t-delta)/T1app)
-            const float FE = ts.A * E;
+            // A * exp(-(t-delta)/T1app)
+            const float FE = USE_EB ? ts.AE * ebt : ts.A * fexp2(u * ts.k.nk);
             const float Sd = ts.A - FE;                    // aslrest.py:372
             const float Sp = FE * ts.k.c1;                 // aslrest.py:373 with exp(tau q) folded into c1
             const float dd = -Sd * m.inv_t1b - FE * ts.k.q;
@@ -168,7 +190,7 @@ struct AslRest {
         } else {
             // factor*(exp(r t) - exp(r delt)) = 2 exp(-t q) exp(r delt) * (exp(r u) - 1)/r, which (unlike the
             // reference's float32 form) stays accurate when T1app is close to t1b (r -> 0)
-            const float Be2 = fexp2(t * ts.k.nk) * ts.A;   // 2 exp(-t/T1app) exp(r delt)
+            const float Be2 = (USE_EB ? ebt : fexp2(t * ts.k.nk)) * ts.A;   // 2 exp(-t/T1app) exp(r delt)
             const float e1u = em1r(ts.k.r, u);
             const float Sd = Be2 * e1u;                    // aslrest.py:379
             const float Sp = Be2 * ts.k.e1tau;             // aslrest.py:380
@@ -182,23 +204,25 @@ struct AslRest {
         }
     }
 
-    // prediction at time t and d pred / d x[p]
-    static SVB_HD void eval(const DevModel &m, const Sample &s, float t, float &pred, float *d) {
+    // prediction at time t and the RAW derivative terms: d[] lacks the per-sample factors (pv, pv*f, fblood,
+    // dq/dt1) that scale_grads() applies once per sample after the time loop
+    template <bool USE_EB>
+    static SVB_HD void eval(const DevModel &m, const Vox &v, const Sample &s, float t, int b, float &pred, float *d) {
         pred = 0.0f;
         if (TISS) {
             float S, dd, dq = 0.0f;
-            tissue_eval<T1>(m, s.gm, t, S, dd, dq);
+            tissue_eval<T1, USE_EB>(m, s.gm, t, USE_EB ? v.eb[USE_EB ? b : 0] : 0.0f, S, dd, dq);
             pred = s.gm.pvf * S;
-            d[ix(I_FTISS)] = s.gm.pv * S;
-            if (ATT) d[ix(I_DELT)] = s.gm.pvf * dd;
-            if (T1) d[ix(I_T1)] = s.gm.pvf * dq * s.gm.dqdt1;
+            d[ix(I_FTISS)] = S;
+            if (ATT) d[ix(I_DELT)] = dd;
+            if (T1) d[ix(I_T1)] = dq;
             if (INCWM) {
                 float Sw, ddw, dqw = 0.0f;
-                tissue_eval<(I_T1WM >= 0)>(m, s.wm, t, Sw, ddw, dqw);
+                tissue_eval<(I_T1WM >= 0), USE_EB>(m, s.wm, t, USE_EB ? v.ebw[USE_EB ? b : 0] : 0.0f, Sw, ddw, dqw);
                 pred += s.wm.pvf * Sw;
-                if (INFWM) d[ix(I_FWM)] = s.wm.pv * Sw;
-                if (I_DELTWM >= 0) d[ix(I_DELTWM)] = s.wm.pvf * ddw;
-                if (I_T1WM >= 0) d[ix(I_T1WM)] = s.wm.pvf * dqw * s.wm.dqdt1;
+                if (INFWM) d[ix(I_FWM)] = Sw;
+                if (I_DELTWM >= 0) d[ix(I_DELTWM)] = ddw;
+                if (I_T1WM >= 0) d[ix(I_T1WM)] = dqw;
             } else if (I_T1WM >= 0) {
                 d[ix(I_T1WM)] = 0.0f;
             }
@@ -221,20 +245,33 @@ struct AslRest {
             const float dA = active ? (dkc * h + kc * g * dz) : 0.0f;
             pred += s.fb * A;
             d[ix(I_FBLOOD)] = A;
-            if (I_DELTBLOOD >= 0) d[ix(I_DELTBLOOD)] = s.fb * dA;
+            if (I_DELTBLOOD >= 0) d[ix(I_DELTBLOOD)] = dA;
         }
+    }
+
+    // per-sample factors of the raw derivative sums G[p] = sum_b r_b d_b[p]
+    static SVB_HD void scale_grads(const Sample &s, float *G) {
+        if (TISS) {
+            G[ix(I_FTISS)] *= s.gm.pv;
+            if (ATT) G[ix(I_DELT)] *= s.gm.pvf;
+            if (T1) G[ix(I_T1)] *= s.gm.pvf * s.gm.dqdt1;
+            if (INFWM) G[ix(I_FWM)] *= s.wm.pv;
+            if (I_DELTWM >= 0) G[ix(I_DELTWM)] *= s.wm.pvf;
+            if (I_T1WM >= 0 && INCWM) G[ix(I_T1WM)] *= s.wm.pvf * s.wm.dqdt1;
+        }
+        if (ART && I_DELTBLOOD >= 0) G[ix(I_DELTBLOOD)] *= s.fb;
     }
 
     // forward value only (Model.evaluate)
     static SVB_HD float predict(const DevModel &m, const Vox &v, const float *x, float t) {
         Sample s = prep_sample(m, v, x);
         float pred, d[PA];
-        eval(m, s, t, pred, d);
+        eval<false>(m, v, s, t, 0, pred, d);
         return pred;
     }
 
     // Visit every time point of the batch.  Acc supplies: static NB (compile-time batch size, 0 = dynamic),
-    // n(), time(b) and add(b, pred, d).
+    // n(), time(b), add(b, pred, d) and the accumulated G[].
     template <class Acc>
     static SVB_HD void run(const DevModel &m, const Vox &v, const float *x, Acc &acc) {
         Sample s = prep_sample(m, v, x);
@@ -242,17 +279,18 @@ struct AslRest {
 #pragma unroll
             for (int b = 0; b < (Acc::NB > 0 ? Acc::NB : 1); ++b) {
                 float pred, d[PA];
-                eval(m, s, acc.time(b), pred, d);
+                eval<use_eb<Acc>()>(m, v, s, acc.time(b), b, pred, d);
                 acc.add(b, pred, d);
             }
         } else {
             const int nb = acc.n();
             for (int b = 0; b < nb; ++b) {
                 float pred, d[PA];
-                eval(m, s, acc.time(b), pred, d);
+                eval<false>(m, v, s, acc.time(b), b, pred, d);
                 acc.add(b, pred, d);
             }
         }
+        scale_grads(s, acc.G);
     }
 };
 

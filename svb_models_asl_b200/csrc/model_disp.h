@@ -147,6 +147,8 @@ struct AslDisp {
     struct Vox {
         float pvgm;
     };
+    template <class Acc>
+    static SVB_HD void bind_times(const DevModel &, Vox &, const Acc &) {}
     static SVB_HD Vox load_vox(const DevModel &m, int64_t w) {
         Vox v;
         v.pvgm = m.pvgm ? m.pvgm[w] : m.pvgm_s;

@@ -26,6 +26,8 @@ struct AslNN {
         float a1[H];      // W0[1][j]*delt + b0[j]
     };
 
+    template <class Acc>
+    static SVB_HD void bind_times(const DevModel &, Vox &, const Acc &) {}
     static SVB_HD Vox load_vox(const DevModel &, int64_t) { return Vox(); }
 
     static SVB_HD Sample prep_sample(const DevModel &m, const Vox &, const float *x) {

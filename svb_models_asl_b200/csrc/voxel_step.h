@@ -114,7 +114,10 @@ SVB_HD float sample_theta(const svbasl_engine &e, uint32_t key, int64_t u, int p
     return th;
 }
 
-template <class M, int NBT>
+// LEAN: the production flavour of a step - sample-based latent loss, draws from the in-register Philox stream,
+// no spatial prior - with those three run-time switches resolved at compile time, so the hot loop carries no
+// dead code (the generic flavour's skipped branches cost instruction-cache misses, profiles/r1_notes.md).
+template <class M, int NBT, bool LEAN = false>
 struct VoxelStep {
     static constexpr int P = M::P;
     static constexpr int N = P + 1;                 // noise last
@@ -155,11 +158,13 @@ struct VoxelStep {
         const float Tf = ec.t_full;
         const float scale = ec.scale;
         const float lw = e.latent_weight;
-        const bool numeric = (e.latent == SVBASL_LATENT_NUMERIC);
+        const bool numeric = LEAN || (e.latent == SVBASL_LATENT_NUMERIC);
+        const bool eps_mem = !LEAN && e.eps != nullptr;
         const uint32_t key = rng_key(e.seed, step);
         typename M::Vox vox = M::load_vox(md, w);
         BatchAcc<P, NBT> acc;
         acc.load(e, w, row0);
+        M::bind_times(md, vox, acc);
 
         float sd[N];
         float pm[N], pinv[N], plog[N], phi_live[N];
@@ -193,7 +198,7 @@ struct VoxelStep {
 
         for (int s = 0; s < S; ++s) {
             float eps[N];
-            if (e.eps) {
+            if (eps_mem) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) eps[j] = e.eps[((int64_t)j * S + s) * e.ld + w];
             } else {
@@ -229,7 +234,7 @@ struct VoxelStep {
             if (numeric) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
-                    if (e.prior_type[i] == SVBASL_PRIOR_MRF) {
+                    if (!LEAN && e.prior_type[i] == SVBASL_PRIOR_MRF) {
                         // -E_s[ 1/2 log ak - ak/4 sum_u (x_w - x_u)^2 ]  (SURVEY Appendix A.5); the neighbours'
                         // samples come from the pre-pass buffer [slot][S][ld]
                         const int slot = ec.sp_slot[i];
@@ -270,7 +275,7 @@ struct VoxelStep {
         if (numeric) {
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                if (e.prior_type[i] != SVBASL_PRIOR_MRF) {
+                if (LEAN || e.prior_type[i] != SVBASL_PRIOR_MRF) {
                     const float q = a_hyp[i];                           // sum_s lw (theta-m)^2 / v
                     cost += 0.5f * q + (float)S * lw * 0.5f * plog[i];
                     a_hyp[i] = 0.5f * (q - (float)S * lw);              // sum_s lw/2 ((theta-m)^2/v - 1)

@@ -17,7 +17,7 @@ def build():
     from svb_models_asl_b200.build import aslrest_flag_sets, disp_flag_sets, variants
     os.makedirs(OUT, exist_ok=True)
     flags = aslrest_flag_sets()
-    fast = [(f, nbt) for (_m, kind, f, nbt, _e) in variants() if kind == 0 and nbt]
+    fast = sorted({(f, nbt) for (_m, kind, f, nbt, _l, _e) in variants() if kind == 0 and nbt})
     hdr = ["// GENERATED", "#define HOSTSIM_ASLREST_FLAGS " + " ".join("X(0x%xu)" % f for f in flags),
            "#define HOSTSIM_DISP_FLAGS " + " ".join("X(0x%xu)" % f for f in disp_flag_sets()),
            "#define HOSTSIM_FAST " + " ".join("Y(0x%xu, %d)" % v for v in fast), ""]

@@ -13,7 +13,7 @@
 
 using namespace svb;
 
-template <class M, int NBT>
+template <class M, int NBT, bool LEAN = false>
 static int run_step(const svbasl_model *md, const svbasl_engine *e, const svbasl_adam *ad, int64_t step0, float *cost,
                     float *grad, double *cost_sum, double *ak_grad) {
     const int n_iters = ad ? ad->n_iters : 1;
@@ -21,7 +21,7 @@ static int run_step(const svbasl_model *md, const svbasl_engine *e, const svbasl
     const EngineConst ec = make_engine_const(*e);
     for (int64_t local = 0; local < e->n_vox; ++local) {
         const int64_t w = e->w_begin + local;
-        VoxelStep<M, NBT> vs;
+        VoxelStep<M, NBT, LEAN> vs;
         vs.load(*e, w);
         for (int it = 0; it < n_iters; ++it) {
             const int64_t step = (ad ? ad->step0 : step0) + it;
@@ -109,6 +109,7 @@ extern "C" int hostsim_step(const svbasl_model *md, const svbasl_engine *e, cons
                             float *cost, float *grad, double *cost_sum, double *ak_grad, int nbt) {
     if (is_nn(md)) {
         if (nbt == 6) return run_step<AslNN, 6>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
+        if (nbt == 106) return run_step<AslNN, 6, true>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
         return run_step<AslNN, 0>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
     }
     if (md->kind == SVBASL_MODEL_ASLREST_DISP) {
@@ -124,7 +125,9 @@ extern "C" int hostsim_step(const svbasl_model *md, const svbasl_engine *e, cons
         HOSTSIM_ASLREST_FLAGS
 #undef X
     }
-#define Y(F, NBT) if (md->kind == SVBASL_MODEL_ASLREST && f == F && nbt == NBT) return run_step<AslRest<F>, NBT>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
+    // nbt = 100 + NBT selects the lean (production) flavour of the same layout
+#define Y(F, NBT) if (md->kind == SVBASL_MODEL_ASLREST && f == F && nbt == NBT) return run_step<AslRest<F>, NBT>(md, e, ad, step, cost, grad, cost_sum, ak_grad); \
+    if (md->kind == SVBASL_MODEL_ASLREST && f == F && nbt == 100 + NBT) return run_step<AslRest<F>, NBT, true>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
     HOSTSIM_FAST
 #undef Y
     return -2;
