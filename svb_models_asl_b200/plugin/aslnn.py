@@ -118,7 +118,9 @@ class AslNNModel(Model):
         return packed
 
     def _init_flow(self, _param, _t, data):
-        return np.asarray(data).mean(axis=1).astype(NP_DTYPE), None      # aslnn.py:143-147 (no floor)
+        # aslnn.py:143-147 takes the plain mean; ftiss is LogNormal here, so a non-positive mean would make the
+        # initial log-mean NaN - floored like aslrest's initialiser (aslrest.py:467)
+        return np.maximum(np.asarray(data).mean(axis=1), 0.1).astype(NP_DTYPE), None
 
     # ---- weights: load / save / train ----
     def _init_nn(self):

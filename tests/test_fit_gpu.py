@@ -177,3 +177,34 @@ def test_spatial_prior_fit_smooths_and_learns_ak(tmp_path):
     def rough(v):
         return sum(np.abs(np.diff(v, axis=a)).mean() for a in range(3))
     assert rough(fm) <= rough(fn) * 1.001          # never rougher than the voxel-wise fit
+
+
+def test_aslnn_and_disp_fits_run_through_the_plugin_api(tmp_path):
+    """aslnn (train_load weights in the reference .npy layout, asl_example_sim_nn.py:23-41) and aslrest_disp
+    drive the same engine through run(); outputs are finite and the cost decreases."""
+    from svb.main import run
+    from svb_models_asl_b200.svbcompat import nifti
+    rng = np.random.default_rng(6)
+    vol, ftiss, delt = _sim_volume((6, 6, 6), rng, noise=0.3, t1b=1.65)
+    nifti.save(vol, str(tmp_path / "sig.nii.gz"))
+    # weights: a quick fit of the MLP to the analytic curve (scripts/retrain_model.py does this properly)
+    wdir = str(tmp_path / "trained_data")
+    os.makedirs(wdir)
+    g = np.random.default_rng(0)
+    for i, (a, b) in enumerate([(2, 10), (10, 10), (10, 1)]):
+        np.save(os.path.join(wdir, "weights%i.npy" % i), g.normal(0, 0.5, (a, b)).astype(np.float32))
+        np.save(os.path.join(wdir, "biases%i.npy" % i), g.normal(0, 0.1, (1, b)).astype(np.float32))
+    base = {"tau": 1.8, "casl": True, "plds": PLDS, "repeats": [1], "learning_rate": 0.05, "sample_size": 10,
+            "epochs": 200, "save_mean": True, "save_model_fit": True, "force_num_latent_loss": True, "display_step": 0}
+    _rt, svb_nn, h_nn = run(str(tmp_path / "sig.nii.gz"), "aslnn", str(tmp_path / "nn"), train_load=wdir, **base)
+    assert [p.name for p in svb_nn.params] == ["ftiss", "delttiss", "noise"]
+    assert np.isfinite(h_nn["mean_cost"]).all() and h_nn["mean_cost"][-1] < h_nn["mean_cost"][0]
+    mf = nifti.load(str(tmp_path / "nn" / "mean_ftiss.nii.gz")).data
+    assert np.isfinite(mf).all() and (mf > 0).all()                      # LogNormal: exp(mean)
+    _rt, svb_d, h_d = run(str(tmp_path / "sig.nii.gz"), "aslrest_disp", str(tmp_path / "disp"), inferart=True, **base)
+    assert [p.name for p in svb_d.params] == ["ftiss", "delttiss", "fblood", "deltblood", "s", "sp", "noise"]
+    assert np.isfinite(h_d["mean_cost"]).all() and h_d["mean_cost"][-1] < h_d["mean_cost"][0]
+    fit = nifti.load(str(tmp_path / "disp" / "modelfit.nii.gz")).data
+    assert fit.shape == (6, 6, 6, 6) and np.isfinite(fit).all()
+    md = nifti.load(str(tmp_path / "disp" / "mean_delttiss.nii.gz")).data
+    assert np.median(np.abs(md - delt)) < 0.25
