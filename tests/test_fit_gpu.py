@@ -206,6 +206,29 @@ def test_aslnn_and_disp_fits_run_through_the_plugin_api(tmp_path):
     assert np.isfinite(h_d["mean_cost"]).all() and h_d["mean_cost"][-1] < h_d["mean_cost"][0]
     fit = nifti.load(str(tmp_path / "disp" / "modelfit.nii.gz")).data
     assert fit.shape == (6, 6, 6, 6) and np.isfinite(fit).all()
-    md = nifti.load(str(tmp_path / "disp" / "mean_delttiss.nii.gz")).data
-    # the data were generated without dispersion, so the dispersed fit's arrival time is biased but must track it
-    assert np.isfinite(md).all() and np.corrcoef(md.ravel(), delt.ravel())[0, 1] > 0.8
+    assert np.isfinite(nifti.load(str(tmp_path / "disp" / "mean_delttiss.nii.gz")).data).all()
+
+
+def test_disp_fit_recovers_parameters_of_dispersed_data(tmp_path):
+    """Data generated BY the dispersion model (fixed Fabber-default s, sp) are recovered by fitting it."""
+    from svb import DataModel
+    from svb.main import run
+    from svb_models_asl import AslRestDisp
+    from svb_models_asl_b200.svbcompat import nifti
+    rng = np.random.default_rng(8)
+    n = 6 * 6 * 6
+    ftiss, delt = rng.uniform(2.0, 20.0, n), rng.uniform(0.6, 2.2, n)
+    gen = AslRestDisp(DataModel(np.zeros((1, 6), dtype=np.float32)), tau=1.8, casl=True, plds=PLDS, repeats=1,
+                      infer_disp_params=False)
+    params = np.stack([ftiss, delt]).astype(np.float32).reshape(2, n, 1, 1)
+    t = np.asarray(gen.tis, dtype=np.float32).reshape(1, 1, -1)
+    sig = gen.ievaluate(params, t)[:, 0, :] + rng.normal(0, 0.1, (n, 6))
+    nifti.save(sig.reshape(6, 6, 6, 6).astype(np.float32), str(tmp_path / "sig.nii.gz"))
+    _rt, svb, hist = run(str(tmp_path / "sig.nii.gz"), "aslrest_disp", str(tmp_path / "out"), tau=1.8, casl=True,
+                         plds=PLDS, repeats=[1], infer_disp_params=False, learning_rate=0.05, sample_size=10,
+                         epochs=600, save_mean=True, force_num_latent_loss=True, display_step=0)
+    assert [p.name for p in svb.params] == ["ftiss", "delttiss", "noise"]
+    mf = nifti.load(str(tmp_path / "out" / "mean_ftiss.nii.gz")).data.ravel()
+    md = nifti.load(str(tmp_path / "out" / "mean_delttiss.nii.gz")).data.ravel()
+    assert np.median(np.abs(mf - ftiss) / ftiss) < 0.05
+    assert np.median(np.abs(md - delt)) < 0.06
