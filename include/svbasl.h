@@ -165,6 +165,20 @@ int svbasl_n_state(const svbasl_model *model, const svbasl_engine *engine);
 int svbasl_evaluate(const svbasl_model *model, const float *params, const float *tpts, float *out,
                     int64_t n_rows, int32_t n_samples, int32_t n_batch, int64_t n_t_rows, void *stream);
 
+/* aslnn on the tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM, weight tile fed by a TMA bulk copy):
+ * the 10x10 hidden layer of AslNNModel.evaluate (aslnn.py:238-260) as a batched GEMM over tiles of 128 rows, with a
+ * hi/lo operand split that keeps float32-level accuracy (csrc/nn_tc.cu).
+ *   svbasl_nn_pack_weights: HOST helper - writes the 512-float B-operand tile for model->nn_weights.
+ *   svbasl_nn_evaluate_tc:  b_tile = that tile in DEVICE memory; params [2][n_rows] (ftiss, delttiss), tpts
+ *   [n_t_rows][B], out [n_rows][B]; hidden (optional, may be NULL) [n_rows*B][10] receives the second-layer
+ *   pre-activations; status (device int32, may be NULL) is set non-zero if a bounded wait on the tensor core
+ *   expired (results are then invalid).  Same shapes and result as svbasl_evaluate for SVBASL_MODEL_ASLNN. */
+#define SVBASL_NN_BTILE_FLOATS 512
+int svbasl_nn_pack_weights(const svbasl_model *model, float *host_tile);
+int svbasl_nn_evaluate_tc(const svbasl_model *model, const float *b_tile, const float *params, const float *tpts,
+                          float *out, float *hidden, int64_t n_rows, int32_t n_batch, int64_t n_t_rows,
+                          int32_t *status, void *stream);
+
 /* One evaluation of the per-voxel cost (negative free energy) and its gradient with respect to the
  * posterior state - the body of svb's sess.run(cost/gradients) for this plugin family.
  * cost [ld] per-voxel cost (may be NULL); grad [n_state][ld] = grad_scale * d(sum cost)/d(state);

@@ -74,6 +74,9 @@ _EXPORTS = {
     "svbasl_n_state": (C.c_int, [C.POINTER(Model), C.POINTER(Engine)]),
     "svbasl_evaluate": (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                   C.c_int32, C.c_int64, C.c_void_p]),
+    "svbasl_nn_pack_weights": (C.c_int, [C.POINTER(Model), C.c_void_p]),
+    "svbasl_nn_evaluate_tc": (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "svbasl_elbo_grad": (C.c_int, [C.POINTER(Model), C.POINTER(Engine), C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
     "svbasl_step": (C.c_int, [C.POINTER(Model), C.POINTER(Engine), C.POINTER(Adam), C.c_void_p, C.c_void_p,

@@ -10,6 +10,12 @@
 
 namespace svb {
 
+// csrc/nn_tc.cu
+struct NnTcArgs;
+void nn_tc_build_b_tile(const NNWeights &w, float *tile);
+int nn_tc_launch(const DevModel &dm, const float *b_tile, const float *params, const float *tpts, float *out,
+                 float *hidden, int64_t n_rows, int32_t n_batch, int64_t n_t_rows, int32_t *status, cudaStream_t st);
+
 static thread_local char g_err[512] = "";
 
 void set_error(const char *fmt, ...) {
@@ -234,6 +240,32 @@ int svbasl_evaluate(const svbasl_model *model, const float *params, const float 
     a.n_samples = n_samples;
     a.n_batch = n_batch;
     return k->eval(a, (cudaStream_t)stream);
+}
+
+int svbasl_nn_pack_weights(const svbasl_model *model, float *host_tile) {
+    if (!model || !host_tile || model->kind != SVBASL_MODEL_ASLNN || !model->nn_weights) {
+        set_error("nn_pack_weights needs an aslnn model with weights");
+        return SVBASL_E_INVALID;
+    }
+    const DevModel dm = make_dev_model(*model);
+    nn_tc_build_b_tile(dm.nn, host_tile);
+    return 0;
+}
+
+int svbasl_nn_evaluate_tc(const svbasl_model *model, const float *b_tile, const float *params, const float *tpts,
+                          float *out, float *hidden, int64_t n_rows, int32_t n_batch, int64_t n_t_rows,
+                          int32_t *status, void *stream) {
+    if (!model || model->kind != SVBASL_MODEL_ASLNN || !model->nn_weights || !b_tile || !params || !tpts ||
+        (!out && !hidden)) {
+        set_error("bad nn_evaluate_tc arguments");
+        return SVBASL_E_INVALID;
+    }
+    if (n_rows < 0 || n_batch < 1 || n_t_rows < 1 || (n_rows % n_t_rows) != 0) {
+        set_error("bad shapes: rows=%lld B=%d t_rows=%lld", (long long)n_rows, n_batch, (long long)n_t_rows);
+        return SVBASL_E_INVALID;
+    }
+    return nn_tc_launch(make_dev_model(*model), b_tile, params, tpts, out, hidden, n_rows, n_batch, n_t_rows, status,
+                        (cudaStream_t)stream);
 }
 
 static int run_step(const svbasl_model *model, const svbasl_engine *engine, const svbasl_adam *adam, int64_t step,

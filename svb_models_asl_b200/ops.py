@@ -67,6 +67,58 @@ def evaluate_model(model, params, tpts):
     return out
 
 
+_NN_TILES = {}
+
+
+def nn_evaluate_tc(model, params, tpts, want_hidden=False):
+    """AslNNModel.evaluate with the 10x10 hidden layer on the tensor cores (tcgen05 / TMEM / TMA, csrc/nn_tc.cu).
+    Same arguments and result as evaluate_model(); optionally also returns the hidden pre-activations [W,S,B,10]."""
+    lib = _require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if isinstance(params, (list, tuple)):
+        cols = [device_array(p, dev) for p in params]
+        shape = torch.broadcast_shapes(*[c.shape for c in cols])
+        par = torch.stack([c.expand(shape) for c in cols], 0)
+    else:
+        par = device_array(params, dev)
+    t = device_array(tpts, dev)
+    if par.ndim == 4:
+        par = par[..., 0]
+    elif par.ndim == 2:
+        par = par[..., None]
+    P, W, S = par.shape
+    if P != 2:
+        raise ValueError("aslnn takes 2 parameters (ftiss, delttiss)")
+    if t.ndim == 3:
+        t = t.reshape(t.shape[0], t.shape[-1])
+    elif t.ndim == 1:
+        t = t.reshape(1, -1)
+    Wt, B = t.shape
+    if Wt not in (1, W):
+        raise ValueError("time points have %i rows but parameters have %i voxels" % (Wt, W))
+    m, keep = model.kernel_model(None)
+    key = (id(model), dev.index, keep[0].tobytes())
+    if key not in _NN_TILES:
+        host = np.zeros(512, dtype=np.float32)
+        L.check(lib.svbasl_nn_pack_weights(C.byref(m), host.ctypes.data))
+        _NN_TILES.clear()
+        _NN_TILES[key] = device_array(host, dev)
+    tile = _NN_TILES[key]
+    n_rows = W * S
+    par = par.reshape(2, n_rows).contiguous()
+    t = t.contiguous()
+    out = torch.empty((W, S, B), device=dev, dtype=torch.float32)
+    hidden = torch.empty((W, S, B, 10), device=dev, dtype=torch.float32) if want_hidden else None
+    status = torch.zeros(1, device=dev, dtype=torch.int32)
+    # tpts rows: the kernel indexes time rows by parameter row / (n_rows / n_t_rows); [W,B] tpts repeat over S samples
+    L.check(lib.svbasl_nn_evaluate_tc(C.byref(m), tile.data_ptr(), par.data_ptr(), t.data_ptr(), out.data_ptr(),
+                                      hidden.data_ptr() if want_hidden else None, n_rows, B, Wt, status.data_ptr(),
+                                      _stream_ptr()))
+    if int(status.item()) != 0:
+        raise L.SvbAslError("tensor-core MLP kernel: a bounded wait expired (TMEM/MMA pipeline did not complete)")
+    return (out, hidden) if want_hidden else out
+
+
 class FusedSvb:
     """
     The per-iteration graph of svb's SvbFit for one shard of voxels, as one kernel launch:

@@ -79,10 +79,12 @@ class AslNNModel(Model):
     # ---- Model API ----
     def evaluate(self, params, tpts):
         """params: ftiss, delttiss each [M,S,1] (or one [2,M,S,1]); tpts [1,1,N] or [M,1,N] -> [M,S,N] CUDA tensor"""
-        from ..ops import evaluate_model
+        from ..ops import evaluate_model, nn_evaluate_tc
         if self.trained_weights is None:
             self._init_nn()
-        return evaluate_model(self, params, tpts)
+        if getattr(self, "use_tensor_cores", True):
+            return nn_evaluate_tc(self, params, tpts)       # hidden layer as tcgen05 GEMM tiles (csrc/nn_tc.cu)
+        return evaluate_model(self, params, tpts)           # FP32-pipe kernel (csrc/model_nn.h)
 
     def tpts(self):
         n_expected = len(self.tis) * self.repeats
