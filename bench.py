@@ -345,6 +345,25 @@ def main():
                               "note": "FP32-pipe roofline 148 SM x 128 lanes x measured SM clock (SURVEY 8d)"}},
         "final_mean_cost": final_cost,
     }
+    if wl["model"] == "aslnn":
+        # Model.evaluate of the surrogate: FP32-pipe kernel vs tcgen05 tensor-core kernel, 200k voxels x S x B rows
+        from svb_models_asl_b200.ops import evaluate_model, nn_evaluate_tc
+        n_ev = 200_000
+        pf = torch.rand(n_ev, 10, 1, device=dev) * 10 + 1
+        pd = torch.rand(n_ev, 10, 1, device=dev) * 2 + 0.3
+        tt = torch.as_tensor(np.asarray(model.tis, dtype=np.float32), device=dev).reshape(1, 1, -1)
+        res = {}
+        for name, fn in (("fp32_pipe", evaluate_model), ("tcgen05", nn_evaluate_tc)):
+            for _ in range(3):
+                fn(model, [pf, pd], tt)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                fn(model, [pf, pd], tt)
+            e1.record()
+            torch.cuda.synchronize()
+            res[name] = {"ms": e0.elapsed_time(e1) / 10, "rows_per_s": n_ev * 60 / (e0.elapsed_time(e1) / 10 * 1e-3)}
+        line["nn_evaluate"] = res
     if not args.no_cpu_baseline:
         rate, sec, threads = cpu_port_rate(args.cpu_voxels, args.cpu_iters)
         line["cpu_baseline"] = {"value": rate, "unit": "voxel-iters/s", "cores": threads, "kind": "port",
