@@ -353,7 +353,7 @@ def main():
         pd = torch.rand(n_ev, 10, 1, device=dev) * 2 + 0.3
         tt = torch.as_tensor(np.asarray(model.tis, dtype=np.float32), device=dev).reshape(1, 1, -1)
         res = {}
-        for name, fn in (("fp32_pipe", evaluate_model), ("tcgen05", nn_evaluate_tc)):
+        for name, fn in (("fp32_pipe", evaluate_model), ("tcgen05", lambda *a: nn_evaluate_tc(*a, check=False))):
             for _ in range(3):
                 fn(model, [pf, pd], tt)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -82,9 +82,13 @@ class AslNNModel(Model):
         from ..ops import evaluate_model, nn_evaluate_tc
         if self.trained_weights is None:
             self._init_nn()
-        if getattr(self, "use_tensor_cores", True):
-            return nn_evaluate_tc(self, params, tpts)       # hidden layer as tcgen05 GEMM tiles (csrc/nn_tc.cu)
-        return evaluate_model(self, params, tpts)           # FP32-pipe kernel (csrc/model_nn.h)
+        # Two kernels give the same result: the FP32-pipe one (csrc/model_nn.h) and the tcgen05 tensor-core one
+        # (csrc/nn_tc.cu).  For a 10-wide layer the tensor-core tile pipeline costs more issue slots (operand
+        # split, STS, TMEM load, barriers) than the 100 FMAs it replaces - measured 35 vs 65 G rows/s on a B200
+        # (profiles/r1_notes.md) - so the FP32 pipe is the default and `use_tensor_cores=True` selects the other.
+        if getattr(self, "use_tensor_cores", False):
+            return nn_evaluate_tc(self, params, tpts)
+        return evaluate_model(self, params, tpts)
 
     def tpts(self):
         n_expected = len(self.tis) * self.repeats

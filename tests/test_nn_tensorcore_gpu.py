@@ -24,7 +24,8 @@ def test_tensor_core_mlp_matches_reference_golden(golden, tmp_path):
     n = golden("aslnn_eval")["nn"]
     ws, bs = [n["w%i" % i] for i in range(3)], [n["b%i" % i] for i in range(3)]
     model = _model(ws, bs, tmp_path)
-    out = model.evaluate(list(n["params"]), n["t"]).cpu().numpy()          # tensor-core path (default)
+    model.use_tensor_cores = True
+    out = model.evaluate(list(n["params"]), n["t"]).cpu().numpy()          # tensor-core path
     ref = n["out64"]
     assert np.abs(out - ref).max() <= 1e-5 * np.abs(ref).max()
     model.use_tensor_cores = False
