@@ -281,39 +281,41 @@ def main():
     assert math.isfinite(final_cost), "non-finite cost"
 
     # ---- end to end through the C ABI with HOST buffers (svb feeds each batch via feed_dict) ----
-    lib = L.load()
-    ctx = C.c_void_p()
-    L.check(lib.svbasl_host_ctx_create(C.byref(ctx), f.ld, f.B))
+    from svb_models_asl_b200.ops import HostFeeder
     rows = list(range(0, f.T, f.n_batches))                           # the time points of batch 0
-    tp_full = np.broadcast_to(model.tpts(), data_host.shape)
     h_data = torch.from_numpy(np.ascontiguousarray(data_host.T[rows])).pin_memory()    # [B, ld]
-    h_tpts = torch.from_numpy(np.ascontiguousarray(tp_full.T[rows])).pin_memory()
-    h_cost = torch.zeros(2, dtype=torch.float64).pin_memory()
-
-    def host_step(i):
-        e = f.engine_desc()
-        ad = f.adam_desc(1)
-        L.check(lib.svbasl_step_host(ctx, C.byref(f.mdesc), C.byref(e), C.byref(ad), h_data.data_ptr(),
-                                     h_tpts.data_ptr(), h_cost.data_ptr() + 8 * (i & 1)))
-        f.step_count += 1
-
+    # time points in the low-rank form the model defines them by (t = ti + z*slicedt, aslrest.py:438-440): the
+    # batch's B inversion times travel with every step, the per-voxel slice offset is resident like the mask
+    lowrank = hasattr(model, "tpts_lowrank")
+    if lowrank:
+        ti_all, zoff = model.tpts_lowrank()
+        h_ti = torch.from_numpy(np.ascontiguousarray(ti_all[rows])).pin_memory()
+        zoff_dev = torch.as_tensor(zoff, device=dev) if zoff is not None else None
+        h_tpts = None
+    else:
+        tp_full = np.broadcast_to(model.tpts(), data_host.shape)
+        h_tpts = torch.from_numpy(np.ascontiguousarray(tp_full.T[rows])).pin_memory()
+        h_ti = zoff_dev = None
     e2e_ok = not f.mrf          # the host-staged entry point does not run the spatial pre-pass / hyper step
+    feeder = HostFeeder(f) if e2e_ok else None
     for i in range(WU if e2e_ok else 0):
-        host_step(i)
-    L.check(lib.svbasl_host_sync(ctx))
+        feeder.step(h_data, h_tpts, h_ti, zoff_dev)
+    if e2e_ok:
+        feeder.sync()
     barrier()
     t0 = time.perf_counter()
     for i in range(K if e2e_ok else 0):
-        host_step(i)
-    L.check(lib.svbasl_host_sync(ctx))
+        feeder.step(h_data, h_tpts, h_ti, zoff_dev)
+    last_cost = feeder.sync() if e2e_ok else 0.0
     e2e_s = max(time.perf_counter() - t0, 1e-9)
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         td.all_reduce(te, op=td.ReduceOp.MAX)
     e2e_s = float(te.item())
-    assert math.isfinite(float(h_cost[0])) and math.isfinite(float(h_cost[1]))
-    L.check(lib.svbasl_host_ctx_destroy(ctx))
-    h2d = 2 * 4 * f.B * f.ld
+    assert math.isfinite(last_cost)
+    if feeder is not None:
+        feeder.close()
+    h2d = 4 * f.B * f.ld + (4 * f.B if lowrank else 4 * f.B * f.ld)
 
     if rank != 0:
         if world > 1:
@@ -333,7 +335,8 @@ def main():
         "clocks": clocks,
         "e2e": {"value": (W * world * K / e2e_s) if e2e_ok else None, "unit": "voxel-iters/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 8, "ms_per_step": e2e_s / K * 1e3,
-                "path": "svbasl_step_host: pinned host batch -> H2D -> fused step -> D2H cost, double-buffered"},
+                "path": "svbasl_step_host: pinned host batch (data rows + the batch's TIs) -> H2D -> fused step -> "
+                        "D2H cost, double-buffered"},
         "gpu_launches": K,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "kernel": "step_kernel<%s, B=%d, lean>" % (wl["model"], f.B),

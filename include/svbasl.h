@@ -214,14 +214,18 @@ int svbasl_init_stats(const float *data, const float *tpts, int64_t n_vox, int64
 int svbasl_model_fit(const svbasl_model *model, const svbasl_engine *engine, float *out, void *stream);
 
 /* End-to-end iteration with HOST buffers, as svb feeds each batch through feed_dict: copies the
- * batch rows of data/tpts from pinned host memory, runs svbasl_step, copies the mean cost back.
- * Double-buffered on two internal streams; call svbasl_host_sync() before reading costs. */
+ * batch rows of the data (and their time points) from pinned host memory, runs svbasl_step, copies the summed
+ * cost back.  Double-buffered on two internal streams; call svbasl_host_sync() before reading costs.
+ * Time points: either host_tpts [B][ld] (one value per voxel and batch row), or - when host_tpts is NULL - the
+ * low-rank form the model defines them by (aslrest.py:438-440): host_ti [B] (the batch's TIs, copied each step)
+ * plus engine->zoff (per-voxel slice offset z*slicedt, resident on the device, may be NULL), which halves the
+ * bytes that cross PCIe per step. */
 typedef struct svbasl_host_ctx svbasl_host_ctx;
 int svbasl_host_ctx_create(svbasl_host_ctx **ctx, int64_t ld, int32_t n_batch);
 int svbasl_host_ctx_destroy(svbasl_host_ctx *ctx);
 int svbasl_step_host(svbasl_host_ctx *ctx, const svbasl_model *model, const svbasl_engine *engine,
-                     const svbasl_adam *adam, const float *host_data /*[B][ld]*/, const float *host_tpts /*[B][ld]*/,
-                     double *host_cost_sum /* pinned, [1] */);
+                     const svbasl_adam *adam, const float *host_data /*[B][ld]*/, const float *host_tpts /*[B][ld] or NULL*/,
+                     const float *host_ti /*[B], used when host_tpts == NULL*/, double *host_cost_sum /* pinned, [1] */);
 int svbasl_host_sync(svbasl_host_ctx *ctx);
 
 #ifdef __cplusplus

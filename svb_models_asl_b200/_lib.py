@@ -92,7 +92,7 @@ _EXPORTS = {
     "svbasl_host_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int32]),
     "svbasl_host_ctx_destroy": (C.c_int, [C.c_void_p]),
     "svbasl_step_host": (C.c_int, [C.c_void_p, C.POINTER(Model), C.POINTER(Engine), C.POINTER(Adam), C.c_void_p,
-                                   C.c_void_p, C.c_void_p]),
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "svbasl_host_sync": (C.c_int, [C.c_void_p]),
 }
 

@@ -174,7 +174,7 @@ using namespace svb;
 struct svbasl_host_ctx {
     cudaStream_t copy_stream, run_stream;
     cudaEvent_t copied[2], consumed[2], done;
-    float *d_data[2], *d_tpts[2];
+    float *d_data[2], *d_tpts[2], *d_ti[2];
     double *d_cost;
     int64_t ld;
     int32_t n_batch;
@@ -389,6 +389,7 @@ int svbasl_host_ctx_create(svbasl_host_ctx **out, int64_t ld, int32_t n_batch) {
         CUDA_TRY(cudaEventCreateWithFlags(&c->consumed[i], cudaEventDisableTiming));
         CUDA_TRY(cudaMalloc(&c->d_data[i], sizeof(float) * ld * n_batch));
         CUDA_TRY(cudaMalloc(&c->d_tpts[i], sizeof(float) * ld * n_batch));
+        CUDA_TRY(cudaMalloc(&c->d_ti[i], sizeof(float) * n_batch));
     }
     CUDA_TRY(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&c->d_cost, sizeof(double) * 2));
@@ -403,6 +404,7 @@ int svbasl_host_ctx_destroy(svbasl_host_ctx *c) {
     for (int i = 0; i < 2; ++i) {
         cudaFree(c->d_data[i]);
         cudaFree(c->d_tpts[i]);
+        cudaFree(c->d_ti[i]);
         cudaEventDestroy(c->copied[i]);
         cudaEventDestroy(c->consumed[i]);
     }
@@ -415,20 +417,22 @@ int svbasl_host_ctx_destroy(svbasl_host_ctx *c) {
 }
 
 int svbasl_step_host(svbasl_host_ctx *c, const svbasl_model *model, const svbasl_engine *engine, const svbasl_adam *adam,
-                     const float *host_data, const float *host_tpts, double *host_cost_sum) {
-    if (!c || !engine || !adam || !host_data || !host_tpts) { set_error("null argument"); return SVBASL_E_INVALID; }
+                     const float *host_data, const float *host_tpts, const float *host_ti, double *host_cost_sum) {
+    if (!c || !engine || !adam || !host_data || (!host_tpts && !host_ti)) { set_error("null argument"); return SVBASL_E_INVALID; }
     if (engine->ld != c->ld || engine->n_batch != c->n_batch) { set_error("engine does not match the host context"); return SVBASL_E_INVALID; }
     const int s = c->slot;
     const size_t bytes = sizeof(float) * (size_t)c->ld * (size_t)c->n_batch;
     // the staging slot may only be overwritten once the iteration that used it two calls ago has finished
     if (c->calls >= 2) CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->consumed[s], 0));
     CUDA_TRY(cudaMemcpyAsync(c->d_data[s], host_data, bytes, cudaMemcpyHostToDevice, c->copy_stream));
-    CUDA_TRY(cudaMemcpyAsync(c->d_tpts[s], host_tpts, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    if (host_tpts) CUDA_TRY(cudaMemcpyAsync(c->d_tpts[s], host_tpts, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    else CUDA_TRY(cudaMemcpyAsync(c->d_ti[s], host_ti, sizeof(float) * (size_t)c->n_batch, cudaMemcpyHostToDevice, c->copy_stream));
     CUDA_TRY(cudaEventRecord(c->copied[s], c->copy_stream));
     CUDA_TRY(cudaStreamWaitEvent(c->run_stream, c->copied[s], 0));
     svbasl_engine e = *engine;
     e.data = c->d_data[s];
-    e.tpts = c->d_tpts[s];
+    e.tpts = host_tpts ? c->d_tpts[s] : nullptr;
+    if (!host_tpts) e.ti = c->d_ti[s];            // e.zoff stays the caller's resident per-voxel slice offset
     e.t_row0 = 0;
     e.t_row_stride = 1;
     svbasl_adam ad = *adam;

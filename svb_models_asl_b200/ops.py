@@ -330,3 +330,52 @@ class FusedSvb:
         """Model-space posterior means [P, n_vox] (transform applied) and internal means/variances."""
         sl = slice(self.halo[0], self.halo[0] + self.n_vox)
         return self.state[:self.N, sl], torch.exp(self.state[self.N:2 * self.N, sl])
+
+
+class HostFeeder:
+    """
+    Iterations fed from HOST memory, the way svb feeds every batch through ``feed_dict``: each ``step`` copies the
+    batch's data rows (pinned host memory) to the device on a copy stream while the previous iteration computes,
+    runs the fused step and copies the summed cost back (svbasl_step_host).  Time points travel either as a full
+    [B, ld] array or in the model's low-rank form (the batch's TIs; the per-voxel slice offset stays resident).
+    """
+
+    def __init__(self, fused):
+        self.f = fused
+        self.lib = fused.lib
+        self.ctx = C.c_void_p()
+        L.check(self.lib.svbasl_host_ctx_create(C.byref(self.ctx), fused.ld, fused.B))
+        self.cost = torch.zeros(2, dtype=torch.float64).pin_memory()
+        self.calls = 0
+
+    def step(self, host_data, host_tpts=None, host_ti=None, zoff_dev=None):
+        """host_data [B, ld] (pinned); host_tpts [B, ld] (pinned) or host_ti [B] (pinned) + zoff_dev [ld] or None."""
+        f = self.f
+        if f.mrf:
+            raise ValueError("host-fed steps do not support spatial priors (pre-pass / hyper step run per iteration)")
+        e = f.engine_desc()
+        if host_tpts is None:
+            e.tpts = None
+            e.zoff = zoff_dev.data_ptr() if zoff_dev is not None else None
+        ad = f.adam_desc(1)
+        L.check(self.lib.svbasl_step_host(self.ctx, C.byref(f.mdesc), C.byref(e), C.byref(ad), host_data.data_ptr(),
+                                          host_tpts.data_ptr() if host_tpts is not None else None,
+                                          host_ti.data_ptr() if host_ti is not None else None,
+                                          self.cost.data_ptr() + 8 * (self.calls & 1)))
+        f.step_count += 1
+        self.calls += 1
+
+    def sync(self):
+        L.check(self.lib.svbasl_host_sync(self.ctx))
+        return float(self.cost[(self.calls - 1) & 1]) if self.calls else float("nan")
+
+    def close(self):
+        if self.ctx:
+            self.lib.svbasl_host_ctx_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

@@ -232,3 +232,46 @@ def test_disp_fit_recovers_parameters_of_dispersed_data(tmp_path):
     md = nifti.load(str(tmp_path / "out" / "mean_delttiss.nii.gz")).data.ravel()
     assert np.median(np.abs(mf - ftiss) / ftiss) < 0.05
     assert np.median(np.abs(md - delt)) < 0.06
+
+
+def test_host_fed_steps_equal_device_resident_steps():
+    """svbasl_step_host (batches from pinned host memory, full or low-rank time points) follows exactly the same
+    trajectory as device-resident svbasl_step."""
+    from svb import DataModel
+    from svb_models_asl import AslRestModel
+    from svb_models_asl_b200.ops import HostFeeder
+    from svb_models_asl_b200.svbcompat.fit import SvbFit
+    rng = np.random.default_rng(12)
+    vol, _f, _d = _sim_volume((5, 7, 6), rng, noise=0.5, t1b=1.65, slicedt=0.0452)
+    data = vol.reshape(-1, 6)
+    states = []
+    for mode in ("device", "host_full", "host_lowrank"):
+        dm = DataModel(vol)
+        model = AslRestModel(dm, tau=1.8, casl=True, plds=PLDS, repeats=[1], slicedt=0.0452, inferart=True)
+        fit = SvbFit(dm, model)
+        fit._setup(model.tpts(), dm.data_flattened, None, 10, 0.05, epochs=20, force_num_latent_loss=True)
+        f = fit.fused
+        if mode == "device":
+            for _ in range(7):
+                f.step(1)
+        else:
+            feeder = HostFeeder(f)
+            h_data = torch.from_numpy(np.ascontiguousarray(dm.data_flattened.T)).pin_memory()
+            if mode == "host_full":
+                h_t = torch.from_numpy(np.ascontiguousarray(model.tpts().T)).pin_memory()
+                for _ in range(7):
+                    feeder.step(h_data, host_tpts=h_t)
+            else:
+                ti, zoff = model.tpts_lowrank()
+                h_ti = torch.from_numpy(ti).pin_memory()
+                zd = torch.as_tensor(zoff, device=f.dev)
+                for _ in range(7):
+                    feeder.step(h_data, host_ti=h_ti, zoff_dev=zd)
+            cost = feeder.sync()
+            assert np.isfinite(cost)
+            feeder.close()
+        assert f.step_count == 7
+        states.append(f.state.cpu().numpy())
+    np.testing.assert_array_equal(states[0], states[1])
+    # ti + z*slicedt is formed in float32 on the device instead of float64-then-rounded on the host: 1 ulp in t
+    np.testing.assert_allclose(states[2], states[0], rtol=2e-4, atol=2e-5)
