@@ -268,6 +268,7 @@ def main():
     for i in range(K):
         f.step(1)
         ev[i + 1].record()
+    f.finish()
     barrier()
     clocks = sampler.stop()
     total_ms = ev[0].elapsed_time(ev[K])

@@ -196,6 +196,7 @@ class FusedSvb:
         # the adjacent ranks; reduce_fn(tensor) sums a small tensor over all ranks in place
         self.halo_exchange = None
         self.reduce_fn = None
+        self.plan = None            # set by enable_overlap(): boundary-first launches + comm stream
 
     # ---- descriptors ----
     def engine_desc(self, row0=0):
@@ -260,6 +261,8 @@ class FusedSvb:
             raise ValueError("spatial priors couple neighbouring voxels: one iteration per launch")
         if n_iters > self.max_fuse:
             raise ValueError("at most %i fused iterations per launch" % self.max_fuse)
+        if self.mrf and self.plan is not None:
+            return self._step_spatial_sharded(want_cost)
         e = self.engine_desc(row0=self.step_count % self.n_batches)
         ad = self.adam_desc(n_iters)
         if self.mrf:
@@ -276,6 +279,66 @@ class FusedSvb:
         self.step_count += n_iters
         return self.cost_hist[self.step_count - n_iters:self.step_count]
 
+    # ---- spatial prior over several GPUs: boundary voxels first, halo exchange overlapped with the interior ----
+    def enable_overlap(self, plan):
+        """Shard-boundary voxels are processed first so that their new state travels to the neighbouring ranks (NCCL
+        send/recv on a side stream) while the interior is still being computed; the all-reduce of the log-ak
+        gradient and the hyper-parameter step run on the same side stream behind the interior launch."""
+        self.plan = plan
+        self.comm_stream = torch.cuda.Stream(device=self.dev)
+        self.ev_halo = self.ev_ak = None
+        self.ak_grads = [torch.zeros(L.MAX_SPATIAL, device=self.dev, dtype=torch.float64) for _ in range(2)]
+        lo_n, hi_n = plan.prev_halo_hi, plan.next_halo_lo      # owned voxels the neighbours need
+        a = self.halo[0]
+        if lo_n + hi_n >= self.n_vox:
+            self.ranges = [(a, self.n_vox)]
+            self.n_boundary = 1
+        else:
+            self.ranges = [r for r in ((a, lo_n), (a + self.n_vox - hi_n, hi_n)) if r[1] > 0]
+            self.n_boundary = len(self.ranges)
+            self.ranges.append((a + lo_n, self.n_vox - lo_n - hi_n))
+
+    def _step_spatial_sharded(self, want_cost=True):
+        main = torch.cuda.current_stream()
+        comm = self.comm_stream
+        step = self.step_count
+        self.ak_grad = self.ak_grads[step & 1]               # double-buffered: the previous one may still be in flight
+        e = self.engine_desc(row0=step % self.n_batches)
+        ad = self.adam_desc(1)
+        if self.ev_halo is not None:
+            main.wait_event(self.ev_halo)                     # halo state of the current `state` has arrived
+        self.ak_grad.zero_()
+        self.sample_spatial(e, step)                          # owned + halo voxels; does not need log ak
+        if self.ev_ak is not None:
+            main.wait_event(self.ev_ak)                       # log ak of this iteration (previous hyper step)
+        cost_ptr = self.cost_hist.data_ptr() + 8 * step if want_cost else None
+        ev_bnd = torch.cuda.Event()
+        for k, (w0, n) in enumerate(self.ranges):
+            e.w_begin, e.n_vox = w0, n
+            L.check(self.lib.svbasl_step(C.byref(self.mdesc), C.byref(e), C.byref(ad), cost_ptr,
+                                         self.nan_count.data_ptr(), _stream_ptr()))
+            if k == self.n_boundary - 1:
+                ev_bnd.record(main)
+        ev_int = torch.cuda.Event()
+        ev_int.record(main)
+        self.state, self.state_alt = self.state_alt, self.state
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev_bnd)
+            self.plan.exchange_halo(self.state)               # new state of the boundary voxels -> neighbours' halos
+            self.ev_halo = torch.cuda.Event()
+            self.ev_halo.record(comm)
+            comm.wait_event(ev_int)
+            self._hyper_step(self.reduce_fn)                  # all-reduce of d cost / d log ak, then its Adam step
+            self.ev_ak = torch.cuda.Event()
+            self.ev_ak.record(comm)
+        self.step_count += 1
+        return self.cost_hist[step:step + 1]
+
+    def finish(self):
+        """Join the side stream (call before reading state / log_ak after sharded spatial steps)."""
+        if self.plan is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
     def _hyper_step(self, reduce_fn=None):
         if reduce_fn is not None:
             reduce_fn(self.ak_grad)
@@ -290,6 +353,7 @@ class FusedSvb:
 
     def elbo_grad(self, step=None, row0=0):
         """-> (cost [ld], grad [n_state, ld]) without updating anything."""
+        self.finish()
         e = self.engine_desc(row0=row0)
         e.state_out = None
         cost = torch.zeros(self.ld, device=self.dev)
@@ -303,6 +367,7 @@ class FusedSvb:
 
     def model_fit(self):
         """Prediction at the posterior mean for every time point -> [T, ld]"""
+        self.finish()
         e = self.engine_desc()
         out = torch.zeros(self.T, self.ld, device=self.dev)
         L.check(self.lib.svbasl_model_fit(C.byref(self.mdesc), C.byref(e), out.data_ptr(), _stream_ptr()))
@@ -328,6 +393,7 @@ class FusedSvb:
     # ---- results ----
     def posterior_mean(self):
         """Model-space posterior means [P, n_vox] (transform applied) and internal means/variances."""
+        self.finish()
         sl = slice(self.halo[0], self.halo[0] + self.n_vox)
         return self.state[:self.N, sl], torch.exp(self.state[self.N:2 * self.N, sl])
 

@@ -101,6 +101,8 @@ class SvbFit(LogBase):
             self.fused.halo_exchange = plan.exchange_halo
             self.fused.reduce_fn = ShardPlan.allreduce_sum
             plan.exchange_halo(self.fused.state)
+            if kwargs.get("overlap_halo", True):
+                self.fused.enable_overlap(plan)
 
     # ------------------------------------------------------------------
     def train(self, tpts, data, batch_size=None, epochs=100, learning_rate=0.1, sample_size=None, display_step=1,
@@ -145,6 +147,7 @@ class SvbFit(LogBase):
                 # one host sync per displayed epoch; keep display_step large for big fits
                 mc = float(cost_dev[epoch + 1]) / f.n_vox
                 kwargs["log_stream"].write(" - Epoch %04d: mean cost=%f (shard of %i voxels)\n" % (epoch + 1, mc, f.n_vox))
+        f.finish() if hasattr(f, "finish") else None
         torch.cuda.synchronize()
         self.runtime = time.time() - t0
         total = cost_dev.clone()
