@@ -138,6 +138,20 @@ typedef struct svbasl_engine {
     const float *spatial_samples;
     const float *log_ak;           /* [n spatial params] device */
     double *ak_grad;               /* [n spatial params] device accumulators: d(sum cost)/d(log ak) */
+    /* Iteration index from DEVICE memory (CUDA-graph replay: a captured launch cannot change its arguments).
+     * When non-NULL it replaces the `step` argument / adam->step0 everywhere (draws, lr_t index, batch rows) and
+     * `cost_sum` is then the BASE of a per-iteration history indexed by that counter.  svbasl_hyper_step_dev /
+     * svbasl_advance_step increment it at the end of an iteration. */
+    const long long *step_dev;
+    /* Spatial prior across GPUs, fused communication: the updated state of the shard-boundary voxels is ALSO
+     * stored straight into the adjacent ranks' halo columns over NVLink peer memory (pointers obtained by CUDA IPC),
+     * so no separate halo exchange is launched.  peer_lo / peer_hi = the lower / upper neighbour's state_out buffer
+     * (row stride peer_*_ld); local index w is mirrored at peer index w + peer_*_shift when
+     * peer_*_first <= w < peer_*_first + peer_*_count (the owned voxels that lie in that neighbour's halo).  Visibility is ordered by the per-iteration all-reduce
+     * of ak_grad that every rank performs before its next iteration.  NULL = no mirroring. */
+    float *peer_lo, *peer_hi;
+    int64_t peer_lo_ld, peer_hi_ld, peer_lo_shift, peer_hi_shift;
+    int64_t peer_lo_first, peer_lo_count, peer_hi_first, peer_hi_count;
 } svbasl_engine;
 
 /* TensorFlow-form Adam (tf.train.AdamOptimizer): m,v [n_state][ld]; lr_t[step] precomputed on the
@@ -200,6 +214,13 @@ int svbasl_sample_spatial(const svbasl_engine *engine, int64_t n_local, int64_t 
 /* Adam update of the global spatial-precision hyper-parameters from ak_grad (after any allreduce). */
 int svbasl_hyper_step(float *log_ak, float *m, float *v, const double *ak_grad, int32_t n, float grad_scale,
                       float lr_t, float beta1, float beta2, float epsilon, void *stream);
+
+/* Graph-friendly tail of a spatial iteration: Adam on log ak with lr_t[*step_dev] from the device table, then
+ * ak_grad is zeroed for the next iteration and *step_dev += 1. */
+int svbasl_hyper_step_dev(float *log_ak, float *m, float *v, double *ak_grad, int32_t n, float grad_scale,
+                          const float *lr_t, long long *step_dev, float beta1, float beta2, float epsilon, void *stream);
+/* *step_dev += inc (tail of a captured iteration without spatial priors). */
+int svbasl_advance_step(long long *step_dev, long long inc, void *stream);
 
 /* Write the Philox stream the fused kernels consume: eps [P'][S][ld] for `step`. */
 int svbasl_fill_eps(float *eps, int64_t n_vox, int64_t ld, int64_t vox_offset, int32_t n_par, int32_t n_samples,

@@ -52,6 +52,10 @@ class Engine(C.Structure):
         ("t_row0", C.c_int32), ("t_row_stride", C.c_int32),
         ("eps", C.c_void_p), ("seed", C.c_uint64),
         ("neighbours", C.c_void_p), ("spatial_samples", C.c_void_p), ("log_ak", C.c_void_p), ("ak_grad", C.c_void_p),
+        ("step_dev", C.c_void_p),
+        ("peer_lo", C.c_void_p), ("peer_hi", C.c_void_p),
+        ("peer_lo_ld", C.c_int64), ("peer_hi_ld", C.c_int64), ("peer_lo_shift", C.c_int64), ("peer_hi_shift", C.c_int64),
+        ("peer_lo_first", C.c_int64), ("peer_lo_count", C.c_int64), ("peer_hi_first", C.c_int64), ("peer_hi_count", C.c_int64),
     ]
 
 
@@ -84,6 +88,9 @@ _EXPORTS = {
     "svbasl_sample_spatial": (C.c_int, [C.POINTER(Engine), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "svbasl_hyper_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
                                     C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "svbasl_hyper_step_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p,
+                                        C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "svbasl_advance_step": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p]),
     "svbasl_fill_eps": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_uint64,
                                   C.c_int64, C.c_void_p]),
     "svbasl_init_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,

@@ -155,6 +155,26 @@ __global__ void init_stats_kernel(const float *data, const float *tpts, int64_t 
     if (t_at_max) t_at_max[w] = tmx;
 }
 
+// graph-friendly tail: lr_t from the device table at *step_dev, then zero ak_grad and advance the counter
+__global__ void hyper_step_dev_kernel(float *log_ak, float *m, float *v, double *ak_grad, int n, float grad_scale,
+                                      const float *lr_t, long long *step_dev, float b1, float b2, float eps) {
+    const int k = threadIdx.x;
+    const long long step = *step_dev;
+    if (k < n) {
+        const float g = (float)(ak_grad[k] * (double)grad_scale);
+        const float mm = b1 * m[k] + (1.0f - b1) * g;
+        const float vv = b2 * v[k] + (1.0f - b2) * g * g;
+        m[k] = mm;
+        v[k] = vv;
+        log_ak[k] -= lr_t[step] * mm / (sqrtf(vv) + eps);
+        ak_grad[k] = 0.0;
+    }
+    __syncthreads();
+    if (k == 0) *step_dev = step + 1;
+}
+
+__global__ void advance_step_kernel(long long *step_dev, long long inc) { *step_dev += inc; }
+
 __global__ void hyper_step_kernel(float *log_ak, float *m, float *v, const double *ak_grad, int n, float grad_scale,
                                   float lr_t, float b1, float b2, float eps) {
     const int k = threadIdx.x;
@@ -338,6 +358,23 @@ int svbasl_hyper_step(float *log_ak, float *m, float *v, const double *ak_grad, 
     if (!log_ak || !m || !v || !ak_grad || n < 1 || n > SVBASL_MAX_SPATIAL) { set_error("bad hyper_step arguments"); return SVBASL_E_INVALID; }
     hyper_step_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(log_ak, m, v, ak_grad, n, grad_scale, lr_t, beta1, beta2, epsilon);
     return check_launch("hyper_step_kernel");
+}
+
+int svbasl_hyper_step_dev(float *log_ak, float *m, float *v, double *ak_grad, int32_t n, float grad_scale,
+                          const float *lr_t, long long *step_dev, float beta1, float beta2, float epsilon, void *stream) {
+    if (!log_ak || !m || !v || !ak_grad || !lr_t || !step_dev || n < 1 || n > SVBASL_MAX_SPATIAL) {
+        set_error("bad hyper_step_dev arguments");
+        return SVBASL_E_INVALID;
+    }
+    hyper_step_dev_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(log_ak, m, v, ak_grad, n, grad_scale, lr_t, step_dev, beta1,
+                                                              beta2, epsilon);
+    return check_launch("hyper_step_dev_kernel");
+}
+
+int svbasl_advance_step(long long *step_dev, long long inc, void *stream) {
+    if (!step_dev) { set_error("null step counter"); return SVBASL_E_INVALID; }
+    advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, inc);
+    return check_launch("advance_step_kernel");
 }
 
 int svbasl_fill_eps(float *eps, int64_t n_vox, int64_t ld, int64_t vox_offset, int32_t n_par, int32_t n_samples,

@@ -115,8 +115,10 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
     vs.load(a.e, w);
     const int n_iters = update ? a.ad.n_iters : 1;
     int skipped = 0;
+    const int64_t step_base = a.e.step_dev ? (int64_t)*a.e.step_dev : a.step;   // device counter under graph replay
+    double *cost_sum = a.cost_sum ? a.cost_sum + (a.e.step_dev ? step_base : 0) : nullptr;
     for (int it = 0; it < n_iters; ++it) {
-        const int64_t step = a.step + it;
+        const int64_t step = step_base + it;
         const int row0 = (update && a.ad.n_batches > 1) ? (int)(step % a.ad.n_batches) : a.e.t_row0;
         float cost = vs.elbo_grad(a.md, a.e, a.ec, w, step, row0);
         if (update && it == 0) cp_async_wait_all();          // only this thread reads what it copied: no barrier
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
                     // iteration 0 reads the prefetched moments, later fused iterations re-read global memory
                     if (it == 0) vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, it == n_iters - 1, m_sm, v_sm, kBlock);
                     else vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, it == n_iters - 1, a.ad.m + w, a.ad.v + w, a.e.ld);
+                    if (!LEAN && it == n_iters - 1) vs.mirror_to_peers(a.e, w);
                 } else {
                     ++skipped;
                     if (it == n_iters - 1) vs.store_state(a.e, w);
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
         } else {
             cost = 0.0f;
         }
-        if (a.cost_sum) block_accumulate(cost, a.cost_sum + it, red);
+        if (cost_sum) block_accumulate(cost, cost_sum + it, red);
         if (!LEAN && a.e.ak_grad) {
 #pragma unroll
             for (int i = 0; i < VS::N; ++i)
@@ -160,7 +163,7 @@ struct SpatialArgs {
 static __global__ void __launch_bounds__(kBlock) spatial_sample_kernel(const __grid_constant__ SpatialArgs a) {
     const int64_t u = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (u >= a.n_local) return;
-    const uint32_t key = rng_key(a.e.seed, a.step);
+    const uint32_t key = rng_key(a.e.seed, a.e.step_dev ? (int64_t)*a.e.step_dev : a.step);
     for (int p = 0; p < a.e.n_par; ++p) {
         const int slot = a.ec.sp_slot[p];
         if (slot < 0) continue;

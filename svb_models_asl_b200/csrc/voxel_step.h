@@ -408,6 +408,29 @@ struct VoxelStep {
         }
     }
 
+    // Fused halo "exchange": a shard-boundary voxel also stores its updated state into the adjacent rank's halo
+    // columns through NVLink peer memory (svbasl_engine.peer_*).  
+    SVB_HD void mirror_to_peers(const svbasl_engine &e, int64_t w) const {
+        if (e.peer_lo && w >= e.peer_lo_first && w < e.peer_lo_first + e.peer_lo_count)
+            write_rows(e, e.peer_lo + (w + e.peer_lo_shift), e.peer_lo_ld);
+        if (e.peer_hi && w >= e.peer_hi_first && w < e.peer_hi_first + e.peer_hi_count)
+            write_rows(e, e.peer_hi + (w + e.peer_hi_shift), e.peer_hi_ld);
+    }
+
+    SVB_HD void write_rows(const svbasl_engine &e, float *s, int64_t ld) const {
+        int a = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            s[(int64_t)i * ld] = mu[i];
+            s[(int64_t)(N + i) * ld] = lv[i];
+        }
+#pragma unroll
+        for (int k = 0; k < NL; ++k) s[(int64_t)(2 * N + k) * ld] = od[k];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (e.prior_type[i] == SVBASL_PRIOR_ARD) s[(int64_t)(2 * N + NL + a++) * ld] = lphi[i];
+    }
+
     SVB_HD void store_state(const svbasl_engine &e, int64_t w) const {
         float *s = (e.state_out ? e.state_out : e.state) + w;
         int a = 0;

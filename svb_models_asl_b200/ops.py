@@ -173,6 +173,7 @@ class FusedSvb:
         z = lambda *s, dt=torch.float32: torch.zeros(*s, device=self.dev, dtype=dt)  # noqa: E731
         self.state = z(self.n_state, self.ld)
         self.state_alt = z(self.n_state, self.ld) if self.mrf else None
+        self._buf_alt0 = self.state_alt
         self.m = z(self.n_state, self.ld)
         self.v = z(self.n_state, self.ld)
         steps = np.arange(1, max_steps + 1, dtype=np.float64)
@@ -197,6 +198,9 @@ class FusedSvb:
         self.halo_exchange = None
         self.reduce_fn = None
         self.plan = None            # set by enable_overlap(): boundary-first launches + comm stream
+        self.graphs = None          # set by enable_graph(): one CUDA-graph replay per spatial iteration
+        self._capturing = False
+        self.peers = None
 
     # ---- descriptors ----
     def engine_desc(self, row0=0):
@@ -225,6 +229,8 @@ class FusedSvb:
         e.spatial_samples = self.sp_samples.data_ptr() if self.sp_samples is not None else None
         e.log_ak = self.log_ak.data_ptr() if self.log_ak is not None else None
         e.ak_grad = self.ak_grad.data_ptr() if self.ak_grad is not None else None
+        if self.graphs is not None or self._capturing:
+            e.step_dev = self.step_dev.data_ptr()
         return e
 
     def adam_desc(self, n_iters=1):
@@ -261,6 +267,12 @@ class FusedSvb:
             raise ValueError("spatial priors couple neighbouring voxels: one iteration per launch")
         if n_iters > self.max_fuse:
             raise ValueError("at most %i fused iterations per launch" % self.max_fuse)
+        if self.graphs is not None:
+            step = self.step_count
+            self.graphs[step & 1].replay()
+            self.state, self.state_alt = self.state_alt, self.state
+            self.step_count += 1
+            return self.cost_hist[step:step + 1]
         if self.mrf and self.plan is not None:
             return self._step_spatial_sharded(want_cost)
         e = self.engine_desc(row0=self.step_count % self.n_batches)
@@ -334,9 +346,93 @@ class FusedSvb:
         self.step_count += 1
         return self.cost_hist[step:step + 1]
 
+    # ---- spatial prior, CUDA-graph replay, halo "exchange" fused into the step kernel over NVLink peer memory ----
+    def share_state_with_neighbours(self, plan):
+        """Exchange CUDA-IPC handles of both state buffers with the adjacent ranks (once, at set-up) so that the
+        step kernel can store boundary voxels' new state directly into the neighbours' halo columns."""
+        import torch.distributed as td
+        from torch.multiprocessing.reductions import reduce_tensor
+        mine = {"rank": plan.rank, "ld": self.ld, "offset": plan.global_offset,
+                "bufs": [reduce_tensor(self.state), reduce_tensor(self.state_alt)]}
+        everyone = [None] * plan.world
+        td.all_gather_object(everyone, mine)
+        self.peers = {}
+        for side, r in (("lo", plan.rank - 1), ("hi", plan.rank + 1)):
+            if 0 <= r < plan.world:
+                info = everyone[r]
+                bufs = [fn(*args) for fn, args in info["bufs"]]          # peer-mapped tensors (cudaIpcOpenMemHandle)
+                self.peers[side] = {"bufs": bufs, "ld": info["ld"], "shift": plan.global_offset - info["offset"]}
+        self.plan = plan
+        a = self.halo[0]
+        lo_n, hi_n = plan.prev_halo_hi, plan.next_halo_lo
+        self._mirror = {"lo": (a, lo_n), "hi": (a + self.n_vox - hi_n, hi_n)}
+        if lo_n + hi_n >= self.n_vox:
+            self.ranges, self.n_boundary = [(a, self.n_vox)], 1
+        else:
+            self.ranges = [r for r in ((a, lo_n), (a + self.n_vox - hi_n, hi_n)) if r[1] > 0]
+            self.n_boundary = len(self.ranges)
+            self.ranges.append((a + lo_n, self.n_vox - lo_n - hi_n))
+        td.barrier()
+
+    def enable_graph(self):
+        """Capture one spatial iteration (pre-pass, step launches, all-reduce of the log-ak gradient, hyper step +
+        counter advance) as a CUDA graph per state-buffer parity; step() then costs one replay."""
+        if not self.mrf:
+            raise ValueError("graph replay is wired for the spatial-prior iteration (the others are one launch)")
+        if self.plan is not None and self.peers is None:
+            raise ValueError("share_state_with_neighbours() first")
+        self.step_dev = torch.tensor([self.step_count], device=self.dev, dtype=torch.int64)
+        self.ak_grad.zero_()
+        if self.reduce_fn is not None:
+            self.reduce_fn(self.ak_grad)                                  # NCCL communicator warm-up outside capture
+        torch.cuda.synchronize()
+        graphs = []
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _parity in (0, 1):
+                g = torch.cuda.CUDAGraph()
+                self._capturing = True
+                with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                    self._record_iteration()
+                self._capturing = False
+                self.state, self.state_alt = self.state_alt, self.state   # the other parity's buffer roles
+                graphs.append(g)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graphs = graphs
+
+    def _record_iteration(self):
+        e = self.engine_desc(row0=0)
+        ad = self.adam_desc(1)
+        parity_out = self.state_alt
+        if self.peers:
+            for side_name in ("lo", "hi"):
+                if side_name in self.peers:
+                    p = self.peers[side_name]
+                    # the neighbour's buffer that plays the state_out role in the same iteration
+                    idx = 1 if parity_out is self._buf_alt0 else 0
+                    setattr(e, "peer_" + side_name, p["bufs"][idx].data_ptr())
+                    setattr(e, "peer_%s_ld" % side_name, p["ld"])
+                    setattr(e, "peer_%s_shift" % side_name, p["shift"])
+                    first, count = self._mirror[side_name]
+                    setattr(e, "peer_%s_first" % side_name, first)
+                    setattr(e, "peer_%s_count" % side_name, count)
+        self.sample_spatial(e, 0)
+        ranges = self.ranges if self.plan is not None else [(self.halo[0], self.n_vox)]
+        for (w0, n) in ranges:
+            e.w_begin, e.n_vox = w0, n
+            L.check(self.lib.svbasl_step(C.byref(self.mdesc), C.byref(e), C.byref(ad), self.cost_hist.data_ptr(),
+                                         self.nan_count.data_ptr(), _stream_ptr()))
+        if self.reduce_fn is not None:
+            self.reduce_fn(self.ak_grad)
+        L.check(self.lib.svbasl_hyper_step_dev(self.log_ak.data_ptr(), self.ak_m.data_ptr(), self.ak_v.data_ptr(),
+                                               self.ak_grad.data_ptr(), len(self.mrf), 1.0 / self.n_vox_global,
+                                               self.lr_t.data_ptr(), self.step_dev.data_ptr(), self.b1, self.b2,
+                                               self.adam_eps, _stream_ptr()))
+
     def finish(self):
         """Join the side stream (call before reading state / log_ak after sharded spatial steps)."""
-        if self.plan is not None:
+        if self.plan is not None and getattr(self, "comm_stream", None) is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 
     def _hyper_step(self, reduce_fn=None):

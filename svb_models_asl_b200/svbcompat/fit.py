@@ -101,8 +101,14 @@ class SvbFit(LogBase):
             self.fused.halo_exchange = plan.exchange_halo
             self.fused.reduce_fn = ShardPlan.allreduce_sum
             plan.exchange_halo(self.fused.state)
-            if kwargs.get("overlap_halo", True):
+            mode = kwargs.get("halo_mode", "peer")       # "peer": fused stores over NVLink + CUDA graph; "nccl"
+            if mode == "peer":
+                self.fused.share_state_with_neighbours(plan)
+                self.fused.enable_graph()
+            elif kwargs.get("overlap_halo", True):
                 self.fused.enable_overlap(plan)
+        elif "M" in prior_types and kwargs.get("use_graph", True):
+            self.fused.enable_graph()
 
     # ------------------------------------------------------------------
     def train(self, tpts, data, batch_size=None, epochs=100, learning_rate=0.1, sample_size=None, display_step=1,

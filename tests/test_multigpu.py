@@ -25,22 +25,22 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _options(spatial):
-    opts = {"tau": 1.8, "casl": True, "plds": PLDS, "repeats": [1], "learning_rate": 0.05, "sample_size": 10,
+def _options(spatial, halo_mode="peer"):
+    opts = {"halo_mode": halo_mode,"tau": 1.8, "casl": True, "plds": PLDS, "repeats": [1], "learning_rate": 0.05, "sample_size": 10,
             "epochs": 60, "save_mean": True, "force_num_latent_loss": True, "display_step": 0, "inferart": not spatial}
     if spatial:
         opts["param_overrides"] = {"ftiss": {"prior_type": "M"}}
     return opts
 
 
-def _worker(rank, world, port, vol_path, out_dir, spatial):
+def _worker(rank, world, port, vol_path, out_dir, spatial, halo_mode):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as td
     torch.cuda.set_device(rank)
     td.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from svb.main import run
-    _rt, svb, hist = run(vol_path, "aslrest", out_dir, **_options(spatial))
+    _rt, svb, hist = run(vol_path, "aslrest", out_dir, **_options(spatial, halo_mode))
     if rank == 0:
         np.save(os.path.join(out_dir, "mean_cost.npy"), hist["mean_cost"])
         if spatial:
@@ -48,8 +48,10 @@ def _worker(rank, world, port, vol_path, out_dir, spatial):
     td.destroy_process_group()
 
 
-@pytest.mark.parametrize("spatial", [False, True])
-def test_two_gpus_reproduce_one_gpu(tmp_path, spatial):
+@pytest.mark.parametrize("spatial,halo_mode", [(False, "peer"), (True, "peer"), (True, "nccl")])
+def test_two_gpus_reproduce_one_gpu(tmp_path, spatial, halo_mode):
+    """halo_mode "peer": boundary state stored straight into the neighbour's halo over NVLink peer memory by the step
+    kernel, whole iteration replayed as a CUDA graph; "nccl": explicit send/recv exchange on a side stream."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from svb.main import run
@@ -63,7 +65,7 @@ def test_two_gpus_reproduce_one_gpu(tmp_path, spatial):
     _rt, svb1, hist1 = run(vol_path, "aslrest", one, **_options(spatial))
     two = str(tmp_path / "two")
     os.makedirs(two, exist_ok=True)
-    mp.spawn(_worker, args=(2, _free_port(), vol_path, two, spatial), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), vol_path, two, spatial, halo_mode), nprocs=2, join=True)
     f1 = nifti.load(os.path.join(one, "mean_ftiss.nii.gz")).data
     f2 = nifti.load(os.path.join(two, "mean_ftiss.nii.gz")).data
     d1 = nifti.load(os.path.join(one, "mean_delttiss.nii.gz")).data
