@@ -222,6 +222,10 @@ int svbasl_hyper_step_dev(float *log_ak, float *m, float *v, double *ak_grad, in
 /* *step_dev += inc (tail of a captured iteration without spatial priors). */
 int svbasl_advance_step(long long *step_dev, long long inc, void *stream);
 
+/* Let kernels on the current device store into memory of `peer_device` (cudaDeviceEnablePeerAccess; "already
+ * enabled" is not an error).  Needed once before svbasl_engine.peer_lo / peer_hi are used. */
+int svbasl_enable_peer_access(int32_t peer_device);
+
 /* Write the Philox stream the fused kernels consume: eps [P'][S][ld] for `step`. */
 int svbasl_fill_eps(float *eps, int64_t n_vox, int64_t ld, int64_t vox_offset, int32_t n_par, int32_t n_samples,
                     uint64_t seed, int64_t step, void *stream);

@@ -90,6 +90,7 @@ _EXPORTS = {
                                     C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "svbasl_hyper_step_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p,
                                         C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "svbasl_enable_peer_access": (C.c_int, [C.c_int32]),
     "svbasl_advance_step": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p]),
     "svbasl_fill_eps": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_uint64,
                                   C.c_int64, C.c_void_p]),

@@ -371,6 +371,18 @@ int svbasl_hyper_step_dev(float *log_ak, float *m, float *v, double *ak_grad, in
     return check_launch("hyper_step_dev_kernel");
 }
 
+int svbasl_enable_peer_access(int32_t peer_device) {
+    int dev = 0, can = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (peer_device == dev) return 0;
+    CUDA_TRY(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) { set_error("device %d cannot access device %d as a peer", dev, peer_device); return SVBASL_E_UNSUPPORTED; }
+    cudaError_t err = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (err == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    if (err != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(err)); return SVBASL_E_CUDA; }
+    return 0;
+}
+
 int svbasl_advance_step(long long *step_dev, long long inc, void *stream) {
     if (!step_dev) { set_error("null step counter"); return SVBASL_E_INVALID; }
     advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, inc);

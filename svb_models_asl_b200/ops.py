@@ -361,6 +361,8 @@ class FusedSvb:
             if 0 <= r < plan.world:
                 info = everyone[r]
                 bufs = [fn(*args) for fn, args in info["bufs"]]          # peer-mapped tensors (cudaIpcOpenMemHandle)
+                with torch.cuda.device(self.dev):
+                    L.check(self.lib.svbasl_enable_peer_access(bufs[0].device.index))
                 self.peers[side] = {"bufs": bufs, "ld": info["ld"], "shift": plan.global_offset - info["offset"]}
         self.plan = plan
         a = self.halo[0]
