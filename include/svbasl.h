@@ -222,9 +222,15 @@ int svbasl_hyper_step_dev(float *log_ak, float *m, float *v, double *ak_grad, in
 /* *step_dev += inc (tail of a captured iteration without spatial priors). */
 int svbasl_advance_step(long long *step_dev, long long inc, void *stream);
 
-/* Let kernels on the current device store into memory of `peer_device` (cudaDeviceEnablePeerAccess; "already
- * enabled" is not an error).  Needed once before svbasl_engine.peer_lo / peer_hi are used. */
-int svbasl_enable_peer_access(int32_t peer_device);
+/* Device buffers that an adjacent rank (another process, another GPU of the box) can store into: plain cudaMalloc
+ * memory exported as a CUDA IPC handle (64 bytes).  The neighbour opens the handle WITH ITS OWN DEVICE CURRENT
+ * (cudaIpcMemLazyEnablePeerAccess), which is what makes the mapping usable by kernels running on that device -
+ * the pointer it gets goes into svbasl_engine.peer_lo / peer_hi.  alloc/free and open/close pair up. */
+#define SVBASL_IPC_HANDLE_BYTES 64
+int svbasl_shared_alloc(int64_t bytes, void **dev_ptr, unsigned char handle[SVBASL_IPC_HANDLE_BYTES]);
+int svbasl_shared_free(void *dev_ptr);
+int svbasl_shared_open(const unsigned char handle[SVBASL_IPC_HANDLE_BYTES], void **dev_ptr);
+int svbasl_shared_close(void *dev_ptr);
 
 /* Write the Philox stream the fused kernels consume: eps [P'][S][ld] for `step`. */
 int svbasl_fill_eps(float *eps, int64_t n_vox, int64_t ld, int64_t vox_offset, int32_t n_par, int32_t n_samples,

@@ -90,7 +90,10 @@ _EXPORTS = {
                                     C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "svbasl_hyper_step_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p,
                                         C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
-    "svbasl_enable_peer_access": (C.c_int, [C.c_int32]),
+    "svbasl_shared_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "svbasl_shared_free": (C.c_int, [C.c_void_p]),
+    "svbasl_shared_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "svbasl_shared_close": (C.c_int, [C.c_void_p]),
     "svbasl_advance_step": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p]),
     "svbasl_fill_eps": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_uint64,
                                   C.c_int64, C.c_void_p]),

@@ -371,15 +371,41 @@ int svbasl_hyper_step_dev(float *log_ak, float *m, float *v, double *ak_grad, in
     return check_launch("hyper_step_dev_kernel");
 }
 
-int svbasl_enable_peer_access(int32_t peer_device) {
-    int dev = 0, can = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (peer_device == dev) return 0;
-    CUDA_TRY(cudaDeviceCanAccessPeer(&can, dev, peer_device));
-    if (!can) { set_error("device %d cannot access device %d as a peer", dev, peer_device); return SVBASL_E_UNSUPPORTED; }
-    cudaError_t err = cudaDeviceEnablePeerAccess(peer_device, 0);
-    if (err == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
-    if (err != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(err)); return SVBASL_E_CUDA; }
+int svbasl_shared_alloc(int64_t bytes, void **dev_ptr, unsigned char handle[SVBASL_IPC_HANDLE_BYTES]) {
+    if (bytes <= 0 || !dev_ptr || !handle) { set_error("bad shared_alloc arguments"); return SVBASL_E_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == SVBASL_IPC_HANDLE_BYTES, "IPC handle size");
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, (size_t)bytes));
+    CUDA_TRY(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t err = cudaIpcGetMemHandle(&h, p);
+    if (err != cudaSuccess) {
+        cudaFree(p);
+        set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(err));
+        return SVBASL_E_CUDA;
+    }
+    memcpy(handle, &h, sizeof(h));
+    *dev_ptr = p;
+    return 0;
+}
+
+int svbasl_shared_free(void *dev_ptr) {
+    if (dev_ptr) CUDA_TRY(cudaFree(dev_ptr));
+    return 0;
+}
+
+int svbasl_shared_open(const unsigned char handle[SVBASL_IPC_HANDLE_BYTES], void **dev_ptr) {
+    if (!handle || !dev_ptr) { set_error("bad shared_open arguments"); return SVBASL_E_INVALID; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));   // current device = the accessing device
+    *dev_ptr = p;
+    return 0;
+}
+
+int svbasl_shared_close(void *dev_ptr) {
+    if (dev_ptr) CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
     return 0;
 }
 

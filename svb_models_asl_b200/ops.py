@@ -119,6 +119,14 @@ def nn_evaluate_tc(model, params, tpts, want_hidden=False, check=True):
     return (out, hidden) if want_hidden else out
 
 
+class _DevicePointer:
+    """Raw device allocation exposed through __cuda_array_interface__ so torch can alias it (float32, C order)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
 class FusedSvb:
     """
     The per-iteration graph of svb's SvbFit for one shard of voxels, as one kernel launch:
@@ -348,22 +356,40 @@ class FusedSvb:
 
     # ---- spatial prior, CUDA-graph replay, halo "exchange" fused into the step kernel over NVLink peer memory ----
     def share_state_with_neighbours(self, plan):
-        """Exchange CUDA-IPC handles of both state buffers with the adjacent ranks (once, at set-up) so that the
-        step kernel can store boundary voxels' new state directly into the neighbours' halo columns."""
+        """Move both state buffers into IPC-exportable device memory and exchange the handles with the adjacent
+        ranks (once, at set-up), so that the step kernel can store boundary voxels' new state directly into the
+        neighbours' halo columns over NVLink."""
         import torch.distributed as td
-        from torch.multiprocessing.reductions import reduce_tensor
-        mine = {"rank": plan.rank, "ld": self.ld, "offset": plan.global_offset,
-                "bufs": [reduce_tensor(self.state), reduce_tensor(self.state_alt)]}
+        n_bytes = 4 * self.n_state * self.ld
+        self._shared = []
+        handles = []
+        for name in ("state", "state_alt"):
+            ptr = C.c_void_p()
+            handle = (C.c_ubyte * 64)()
+            with torch.cuda.device(self.dev):
+                L.check(self.lib.svbasl_shared_alloc(n_bytes, C.byref(ptr), handle))
+            view = _DevicePointer(ptr.value, (self.n_state, self.ld))
+            t = torch.as_tensor(view, device=self.dev)
+            t.copy_(getattr(self, name))
+            setattr(self, name, t)
+            self._shared.append((ptr, view))
+            handles.append(bytes(handle))
+        self._buf_alt0 = self.state_alt
+        mine = {"rank": plan.rank, "ld": self.ld, "offset": plan.global_offset, "handles": handles}
         everyone = [None] * plan.world
         td.all_gather_object(everyone, mine)
         self.peers = {}
         for side, r in (("lo", plan.rank - 1), ("hi", plan.rank + 1)):
             if 0 <= r < plan.world:
                 info = everyone[r]
-                bufs = [fn(*args) for fn, args in info["bufs"]]          # peer-mapped tensors (cudaIpcOpenMemHandle)
-                with torch.cuda.device(self.dev):
-                    L.check(self.lib.svbasl_enable_peer_access(bufs[0].device.index))
-                self.peers[side] = {"bufs": bufs, "ld": info["ld"], "shift": plan.global_offset - info["offset"]}
+                ptrs = []
+                for h in info["handles"]:
+                    p = C.c_void_p()
+                    buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                    with torch.cuda.device(self.dev):                      # the ACCESSING device must be current
+                        L.check(self.lib.svbasl_shared_open(buf, C.byref(p)))
+                    ptrs.append(p.value)
+                self.peers[side] = {"ptrs": ptrs, "ld": info["ld"], "shift": plan.global_offset - info["offset"]}
         self.plan = plan
         a = self.halo[0]
         lo_n, hi_n = plan.prev_halo_hi, plan.next_halo_lo
@@ -374,6 +400,7 @@ class FusedSvb:
             self.ranges = [r for r in ((a, lo_n), (a + self.n_vox - hi_n, hi_n)) if r[1] > 0]
             self.n_boundary = len(self.ranges)
             self.ranges.append((a + lo_n, self.n_vox - lo_n - hi_n))
+        torch.cuda.synchronize()
         td.barrier()
 
     def enable_graph(self):
@@ -413,7 +440,7 @@ class FusedSvb:
                     p = self.peers[side_name]
                     # the neighbour's buffer that plays the state_out role in the same iteration
                     idx = 1 if parity_out is self._buf_alt0 else 0
-                    setattr(e, "peer_" + side_name, p["bufs"][idx].data_ptr())
+                    setattr(e, "peer_" + side_name, p["ptrs"][idx])
                     setattr(e, "peer_%s_ld" % side_name, p["ld"])
                     setattr(e, "peer_%s_shift" % side_name, p["shift"])
                     first, count = self._mirror[side_name]

@@ -102,7 +102,9 @@ class SvbFit(LogBase):
             self.fused.reduce_fn = ShardPlan.allreduce_sum
             plan.exchange_halo(self.fused.state)
             mode = kwargs.get("halo_mode", "peer")       # "peer": fused stores over NVLink + CUDA graph; "nccl"
-            if mode == "peer":
+            if mode == "none":
+                pass
+            elif mode == "peer":
                 self.fused.share_state_with_neighbours(plan)
                 self.fused.enable_graph()
             elif kwargs.get("overlap_halo", True):
