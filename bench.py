@@ -318,6 +318,7 @@ def main():
         feeder.close()
     h2d = 4 * f.B * f.ld + (4 * f.B if lowrank else 4 * f.B * f.ld)
 
+    f.release()
     if rank != 0:
         if world > 1:
             td.destroy_process_group()

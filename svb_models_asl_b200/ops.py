@@ -459,6 +459,27 @@ class FusedSvb:
                                                self.lr_t.data_ptr(), self.step_dev.data_ptr(), self.b1, self.b2,
                                                self.adam_eps, _stream_ptr()))
 
+    def release(self):
+        """Tear down graph / peer-memory resources (before the process group is destroyed): captured graphs hold
+        NCCL work, neighbours hold mappings of our shared buffers."""
+        import torch.distributed as td
+        torch.cuda.synchronize()
+        self.graphs = None
+        if self.peers is not None:
+            for p in self.peers.values():
+                for ptr in p["ptrs"]:
+                    self.lib.svbasl_shared_close(C.c_void_p(ptr))
+            self.peers = None
+            if td.is_available() and td.is_initialized():
+                td.barrier()                       # every neighbour has closed its mapping of our buffers
+            keep = getattr(self, "_shared", [])
+            self.state, self.state_alt = self.state.clone(), self.state_alt.clone()
+            self._buf_alt0 = self.state_alt
+            for ptr, _view in keep:
+                self.lib.svbasl_shared_free(ptr)
+            self._shared = []
+        torch.cuda.synchronize()
+
     def finish(self):
         """Join the side stream (call before reading state / log_ak after sharded spatial steps)."""
         if self.plan is not None and getattr(self, "comm_stream", None) is not None:

@@ -199,6 +199,11 @@ class SvbFit(LogBase):
         f = self.fused
         return f.model_fit()[:, f.halo[0]:f.halo[0] + f.n_vox].T.cpu().numpy()
 
+    def close(self):
+        """Release graph / peer-memory resources of a sharded fit (results stay readable)."""
+        if self.fused is not None:
+            self.fused.release()
+
     def gather(self, local):
         """Concatenate per-shard [.., n_vox] (last axis = voxels... first axis here) arrays on every rank."""
         if self.world == 1:

@@ -46,6 +46,7 @@ def run(data, model_name, output, mask=None, **kwargs):
         for key in ("voxel_cost", "params"):
             if key in history:
                 history[key] = svb.gather(history[key])
+    svb.close()
     if svb.rank != 0:
         return runtime, svb, history
     os.makedirs(output, exist_ok=True)
