@@ -26,6 +26,7 @@ torch.cuda.synchronize(); td.barrier()
 # 1. plain peer write test through fill_eps into the neighbour's state_alt buffer halo? use a scratch: skip
 f.step_dev = torch.tensor([0], device=f.dev, dtype=torch.int64)
 f._capturing = True
+f._fork_stream = torch.cuda.Stream(device=f.dev)
 for it in range(3):
     log("iter", it, "start")
     f._record_iteration()

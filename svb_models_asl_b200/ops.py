@@ -416,6 +416,7 @@ class FusedSvb:
             self.reduce_fn(self.ak_grad)                                  # NCCL communicator warm-up outside capture
         torch.cuda.synchronize()
         graphs = []
+        self._fork_stream = torch.cuda.Stream(device=self.dev)
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -448,10 +449,27 @@ class FusedSvb:
                     setattr(e, "peer_%s_count" % side_name, count)
         self.sample_spatial(e, 0)
         ranges = self.ranges if self.plan is not None else [(self.halo[0], self.n_vox)]
-        for (w0, n) in ranges:
+
+        def launch(w0, n):
             e.w_begin, e.n_vox = w0, n
             L.check(self.lib.svbasl_step(C.byref(self.mdesc), C.byref(e), C.byref(ad), self.cost_hist.data_ptr(),
                                          self.nan_count.data_ptr(), _stream_ptr()))
+
+        if len(ranges) > 1:
+            # the thin boundary launches run on a forked branch of the graph, concurrently with the interior
+            cur = torch.cuda.current_stream()
+            fork = self._fork_stream
+            ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+            ev_fork.record(cur)
+            fork.wait_event(ev_fork)
+            with torch.cuda.stream(fork):
+                for (w0, n) in ranges[:-1]:
+                    launch(w0, n)
+                ev_join.record(fork)
+            launch(*ranges[-1])
+            cur.wait_event(ev_join)
+        else:
+            launch(*ranges[0])
         if self.reduce_fn is not None:
             self.reduce_fn(self.ak_grad)
         L.check(self.lib.svbasl_hyper_step_dev(self.log_ak.data_ptr(), self.ak_m.data_ptr(), self.ak_v.data_ptr(),
