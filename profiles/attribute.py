@@ -46,14 +46,29 @@ def main(rep, obj, kernel):
     rows = list(csv.reader(src.splitlines()))
     hdr = rows[1]
     ia, ie = hdr.index("Address"), hdr.index("Instructions Executed")
-    ex = []
+    stall_cols = [(c, hdr.index(c)) for c in ("stall_long_sb", "stall_wait", "stall_short_sb", "stall_no_inst",
+                                              "stall_barrier", "stall_math") if c in hdr]
+    ex, stalls = [], []
     for r in rows[2:]:
         if len(r) <= ie or not r[ia].startswith("0x"):
             if ex:
                 break
             continue
         ex.append(int(r[ie]))
+        stalls.append([int(r[i] or 0) for _c, i in stall_cols])
     assert len(ex) == len(instrs), (len(ex), len(instrs))
+    # stall samples are attributed to the instruction that WAITS (the consumer), so a line's long-scoreboard
+    # count says where a load's latency was exposed, not where the load was issued
+    for ci, (cname, _i) in enumerate(stall_cols):
+        tot_s = sum(st[ci] for st in stalls)
+        if not tot_s:
+            continue
+        per = collections.Counter()
+        for st, (_off, op, loc) in zip(stalls, instrs):
+            per[loc] += st[ci]
+        print("-- %s samples by source line (total %d)" % (cname, tot_s))
+        for loc, n in per.most_common(12):
+            print("%-28s %8d %5.1f%%" % ("%s:%d" % loc if loc else "?", n, 100.0 * n / tot_s))
     by_line, by_op, tot = collections.Counter(), collections.Counter(), 0
     for n, (_off, op, loc) in zip(ex, instrs):
         by_line[loc] += n

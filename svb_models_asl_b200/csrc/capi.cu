@@ -44,7 +44,8 @@ static uint32_t canonical_flags(const svbasl_model *m) {
 
 // Best kernel for (model layout, batch size): prefers the compile-time batch size, and the lean (production)
 // flavour when the call allows it.
-static const KernelEntry *find_entry(const svbasl_model *m, int nbt, bool want_eval, bool lean_ok = false) {
+// `flavour`: 0 = generic only, 1 = lean allowed (no spatial prior in use), 2 = lean-spatial allowed.
+static const KernelEntry *find_entry(const svbasl_model *m, int nbt, bool want_eval, int flavour = 0) {
     const uint32_t f = canonical_flags(m);
     const KernelEntry *best = nullptr;
     int best_score = -1;
@@ -56,7 +57,7 @@ static const KernelEntry *find_entry(const svbasl_model *m, int nbt, bool want_e
                 continue;
             }
             if (e->nbt != nbt && e->nbt != 0) continue;
-            if (e->lean && !lean_ok) continue;
+            if (e->lean && e->lean != flavour) continue;
             const int score = (e->nbt == nbt ? 2 : 0) + (e->lean ? 1 : 0);
             if (score > best_score) { best = e; best_score = score; }
         }
@@ -91,8 +92,8 @@ static int validate(const svbasl_model *m, const svbasl_engine *e, const KernelE
         set_error("spatial prior without neighbours / log_ak / spatial_samples (call svbasl_sample_spatial first)");
         return SVBASL_E_INVALID;
     }
-    const KernelEntry *k = find_entry(m, e->n_batch, false,
-                                      lean_ok && !mask && !e->eps && e->latent == SVBASL_LATENT_NUMERIC);
+    const bool production = lean_ok && !e->eps && e->latent == SVBASL_LATENT_NUMERIC;
+    const KernelEntry *k = find_entry(m, e->n_batch, false, production ? (mask ? 2 : 1) : 0);
     if (!k) {
         set_error("no kernel compiled for model kind=%d flags=0x%x", m->kind, canonical_flags(m));
         return SVBASL_E_UNSUPPORTED;

@@ -52,6 +52,14 @@ SVB_HD float ftanh(float x) { return tanhf(x); }
 SVB_HD bool finite_f(float x) { return isfinite(x); }
 #endif
 
+// Wait until this thread's asynchronous global->shared copies (kernels.cuh: Adam moments, neighbour tile) have
+// landed.  No-op on the host.
+SVB_HD void async_copies_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 SVB_HD float fmin2(float a, float b) { return a < b ? a : b; }
 SVB_HD float fmax2(float a, float b) { return a > b ? a : b; }
 

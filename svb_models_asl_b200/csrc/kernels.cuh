@@ -16,6 +16,8 @@ struct StepArgs {
     svbasl_adam ad;
     int32_t update;          // 0: cost + gradient only (svbasl_elbo_grad); 1: fused Adam update (svbasl_step)
     int32_t n_state;         // rows of state / m / v
+    int32_t nb_param;        // spatial parameter whose neighbour samples are staged in shared memory, -1 = none
+                             // (chosen by launch_step)
     int64_t step;            // iteration index of the first fused iteration (RNG counter / lr_t index)
     float *cost;             // [ld] or NULL
     float *grad;             // [n_state][ld] or NULL
@@ -46,7 +48,8 @@ struct KernelEntry {
     int32_t kind;
     uint32_t flags;          // canonical SVBASL_F_* set
     int32_t nbt;             // compile-time batch size, 0 = any
-    int32_t lean;            // 1: production flavour (update, Philox, numeric latent loss, no spatial prior, no outputs)
+    int32_t lean;            // flavour: 0 generic; 1 production (update, Philox, numeric latent loss, no spatial
+                             // prior, no per-voxel outputs); 2 production with the spatial prior
     int32_t n_params;
     step_launcher_t step;
     eval_launcher_t eval;    // only on the nbt == 0, mrfmask == 0 entry
@@ -76,14 +79,15 @@ __device__ __forceinline__ void block_accumulate(float v, double *dst, float *sm
 
 // 4-byte asynchronous global->shared copy (LDGSTS): the data lands in shared memory without passing through
 // a register, so a load issued before the sample loop costs nothing while the loop runs.
-__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+__device__ __forceinline__ void cp_async4(unsigned smem_dst, const float *gsrc) {     // smem_dst: shared-window address
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // Fused iteration.  Dynamic shared memory: [2][n_state][kBlock] floats when updating (the Adam moments of this
-// CTA's voxels, prefetched asynchronously at kernel start and consumed after the sample loop), else unused.
+// CTA's voxels, prefetched asynchronously at kernel start and consumed after the sample loop), followed - when
+// a.nb_param >= 0 - by [S][6][kBlock] floats: the six neighbours' samples of spatial parameter nb_param, gathered
+// asynchronously so that the sample loop reads them from shared memory.
 // Resident CTAs per SM the register allocation is tuned for: 4 (<= 128 registers) for the common layouts,
 // fewer for the wide posteriors (P' >= 6: the Cholesky factor and its gradient alone are P'(P'+1) registers).
 template <class M>
@@ -91,12 +95,14 @@ constexpr int min_blocks() {
     return M::kRegHeavy ? 3 : (M::P + 1 <= 5 ? 4 : (M::P + 1 <= 7 ? 3 : 2));
 }
 
-// LEAN = production flavour: fused update, no per-voxel cost / gradient outputs (see VoxelStep)
-template <class M, int NBT, bool LEAN>
+// FL != 0: production flavours - fused update, no per-voxel cost / gradient outputs (see VoxelStep)
+template <class M, int NBT, int FL>
 __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ float mv_tile[];
     __shared__ float red[kBlock / 32];
-    typedef VoxelStep<M, NBT, LEAN> VS;
+    typedef VoxelStep<M, NBT, FL> VS;
+    constexpr bool LEAN = FL != 0;
+    constexpr bool SPATIAL = FL != 1;
     const bool update = LEAN || a.update;
     const int64_t local = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool live = local < a.e.n_vox;
@@ -104,15 +110,46 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
     const int n_state = a.n_state;
     float *m_sm = mv_tile + threadIdx.x;
     float *v_sm = mv_tile + (size_t)n_state * kBlock + threadIdx.x;
-    if (update) {
-        const float *mg = a.ad.m + w, *vg = a.ad.v + w;
-        for (int k = 0; k < n_state; ++k) {
-            cp_async4(m_sm + k * kBlock, mg + (int64_t)k * a.e.ld);
-            cp_async4(v_sm + k * kBlock, vg + (int64_t)k * a.e.ld);
-        }
+    // Prologue order: every independent global load is issued before anything waits on one - the six neighbour
+    // indices, then the posterior state (vs.load), then the asynchronous copies.  (With the index loads inside
+    // the copy loop a warp spent 14 % of its life on six serialised DRAM round trips, profiles/r1_notes.md.)
+    int nb_u[6];
+    const bool tile = SPATIAL && a.nb_param >= 0;
+    if (tile) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) nb_u[k] = a.e.neighbours[(int64_t)k * a.e.ld + w];
     }
     VS vs;
     vs.load(a.e, w);
+    const unsigned sm0 = (unsigned)__cvta_generic_to_shared(mv_tile) + 4u * threadIdx.x;
+    constexpr unsigned kRow = 4u * kBlock;                       // bytes per shared-memory row
+    if (update) {
+        const float *mg = a.ad.m + w, *vg = a.ad.v + w;
+        unsigned dm = sm0, dv = sm0 + (unsigned)n_state * kRow;
+        for (int k = 0; k < n_state; ++k, dm += kRow, dv += kRow, mg += a.e.ld, vg += a.e.ld) {
+            cp_async4(dm, mg);
+            cp_async4(dv, vg);
+        }
+    }
+    NbTile nbt = {nullptr, 0, -1, 0u};
+    if (tile) {
+        const size_t off = update ? 2 * (size_t)n_state * kBlock : 0;
+        const int S = a.e.n_samples;
+        const float *src = a.e.spatial_samples + (int64_t)a.ec.sp_slot[a.nb_param] * S * a.e.ld;
+        unsigned dst = sm0 + (unsigned)off * 4u;
+        uint32_t mask = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) mask |= (nb_u[k] >= 0 ? 1u : 0u) << k;
+        for (int s = 0; s < S; ++s, src += a.e.ld, dst += 6u * kRow) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                if ((mask >> k) & 1u) cp_async4(dst + k * kRow, src + nb_u[k]);
+        }
+        nbt.v = mv_tile + off + threadIdx.x;
+        nbt.stride = kBlock;
+        nbt.param = a.nb_param;
+        nbt.mask = mask;
+    }
     const int n_iters = update ? a.ad.n_iters : 1;
     int skipped = 0;
     const int64_t step_base = a.e.step_dev ? (int64_t)*a.e.step_dev : a.step;   // device counter under graph replay
@@ -120,7 +157,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
     for (int it = 0; it < n_iters; ++it) {
         const int64_t step = step_base + it;
         const int row0 = (update && a.ad.n_batches > 1) ? (int)(step % a.ad.n_batches) : a.e.t_row0;
-        float cost = vs.elbo_grad(a.md, a.e, a.ec, w, step, row0);
+        float cost = vs.elbo_grad(a.md, a.e, a.ec, w, step, row0, nbt);
         if (update && it == 0) cp_async_wait_all();          // only this thread reads what it copied: no barrier
         if (live) {
             if (!LEAN && a.cost) a.cost[w] = cost;
@@ -130,7 +167,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
                     // iteration 0 reads the prefetched moments, later fused iterations re-read global memory
                     if (it == 0) vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, it == n_iters - 1, m_sm, v_sm, kBlock);
                     else vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, it == n_iters - 1, a.ad.m + w, a.ad.v + w, a.e.ld);
-                    if (!LEAN && it == n_iters - 1) vs.mirror_to_peers(a.e, w);
+                    if (SPATIAL && it == n_iters - 1) vs.mirror_to_peers(a.e, w);
                 } else {
                     ++skipped;
                     if (it == n_iters - 1) vs.store_state(a.e, w);
@@ -141,7 +178,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
             cost = 0.0f;
         }
         if (cost_sum) block_accumulate(cost, cost_sum + it, red);
-        if (!LEAN && a.e.ak_grad) {
+        if (SPATIAL && a.e.ak_grad) {
 #pragma unroll
             for (int i = 0; i < VS::N; ++i)
                 if (a.e.prior_type[i] == SVBASL_PRIOR_MRF)
@@ -214,21 +251,30 @@ __global__ void __launch_bounds__(kBlock) fit_kernel(const __grid_constant__ Fit
 inline int check_launch(const char *what);
 void set_error(const char *fmt, ...);
 
-template <class M, int NBT, bool LEAN>
-int launch_step(const StepArgs &a, cudaStream_t st) {
+template <class M, int NBT, int FL>
+int launch_step(const StepArgs &a0, cudaStream_t st) {
+    StepArgs a = a0;
     const unsigned grid = (unsigned)((a.e.n_vox + kBlock - 1) / kBlock);
     if (grid == 0) return 0;
-    const size_t smem = a.update ? sizeof(float) * 2 * (size_t)a.n_state * kBlock : 0;
+    size_t smem = a.update ? sizeof(float) * 2 * (size_t)a.n_state * kBlock : 0;
+    a.nb_param = -1;
+    if (FL != 1) {
+        // neighbour tile of the first spatial parameter, if the planned number of resident CTAs still fits
+        const size_t tile = sizeof(float) * 6 * (size_t)a.e.n_samples * kBlock;
+        for (int i = 0; i < a.e.n_par && i < SVBASL_MAX_PAR && a.nb_param < 0; ++i)
+            if (a.e.prior_type[i] == SVBASL_PRIOR_MRF && (smem + tile + 1024) * min_blocks<M>() <= 227 * 1024) a.nb_param = i;
+        if (a.nb_param >= 0) smem += tile;
+    }
     static size_t smem_allowed = 48 * 1024;                    // per instantiation
     if (smem > smem_allowed) {
-        cudaError_t err = cudaFuncSetAttribute(step_kernel<M, NBT, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t err = cudaFuncSetAttribute(step_kernel<M, NBT, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) {
             set_error("step_kernel: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(err));
             return SVBASL_E_CUDA;
         }
         smem_allowed = smem;
     }
-    step_kernel<M, NBT, LEAN><<<grid, kBlock, smem, st>>>(a);
+    step_kernel<M, NBT, FL><<<grid, kBlock, smem, st>>>(a);
     return check_launch("step_kernel");
 }
 

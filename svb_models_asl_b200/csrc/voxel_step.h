@@ -114,11 +114,24 @@ SVB_HD float sample_theta(const svbasl_engine &e, uint32_t key, int64_t u, int p
     return th;
 }
 
-// LEAN: the production flavour of a step - sample-based latent loss, draws from the in-register Philox stream,
-// no spatial prior - with those three run-time switches resolved at compile time, so the hot loop carries no
-// dead code (the generic flavour's skipped branches cost instruction-cache misses, profiles/r1_notes.md).
-template <class M, int NBT, bool LEAN = false>
+// The neighbours' samples of ONE spatial parameter, staged per thread (kernels.cuh copies them into shared memory
+// asynchronously at kernel start): v[(s*6 + k) * stride] = sample s of neighbour k, mask bit k = neighbour exists.
+// v == nullptr: no tile, elbo_grad gathers from e.spatial_samples where it needs them.
+struct NbTile {
+    const float *v;
+    int stride;
+    int param;
+    uint32_t mask;
+};
+
+// FL, the flavour of a step: 0 = generic (every run-time switch live); 1 = lean, the production flavour -
+// sample-based latent loss, draws from the in-register Philox stream, no spatial prior - with those three
+// switches resolved at compile time, so the hot loop carries no dead code (the generic flavour's skipped
+// branches cost instruction-cache misses, profiles/r1_notes.md); 2 = lean with the spatial prior kept.
+template <class M, int NBT, int FL = 0>
 struct VoxelStep {
+    static constexpr bool LEAN = FL != 0;           // numeric latent loss + Philox draws fixed at compile time
+    static constexpr bool SPATIAL = FL != 1;
     static constexpr int P = M::P;
     static constexpr int N = P + 1;                 // noise last
     static constexpr int NL = N * (N - 1) / 2;
@@ -153,7 +166,7 @@ struct VoxelStep {
 
     // Cost of this voxel for one batch, gradients left in g_*.  Returns the un-scaled cost.
     SVB_HD float elbo_grad(const DevModel &md, const svbasl_engine &e, const EngineConst &ec, int64_t w, int64_t step,
-                           int row0) {
+                           int row0, const NbTile nbt = NbTile{nullptr, 0, -1, 0u}) {
         const int S = e.n_samples;
         const float Tf = ec.t_full;
         const float scale = ec.scale;
@@ -234,7 +247,7 @@ struct VoxelStep {
             if (numeric) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
-                    if (!LEAN && e.prior_type[i] == SVBASL_PRIOR_MRF) {
+                    if (SPATIAL && e.prior_type[i] == SVBASL_PRIOR_MRF) {
                         // -E_s[ 1/2 log ak - ak/4 sum_u (x_w - x_u)^2 ]  (SURVEY Appendix A.5); the neighbours'
                         // samples come from the pre-pass buffer [slot][S][ld]
                         const int slot = ec.sp_slot[i];
@@ -242,13 +255,26 @@ struct VoxelStep {
                         const float ak = fexp(lak);
                         const float *nbs = e.spatial_samples + ((int64_t)slot * S + s) * e.ld;
                         float sdx = 0.0f, sdx2 = 0.0f;
+                        if (nbt.v && nbt.param == i) {
+                            if (s == 0) async_copies_wait();
+                            const float *nv = nbt.v + (int64_t)s * 6 * nbt.stride;
 #pragma unroll
-                        for (int nbr = 0; nbr < 6; ++nbr) {
-                            const int u = e.neighbours[(int64_t)nbr * e.ld + w];
-                            if (u >= 0) {
-                                const float dxu = th[i] - nbs[u];
-                                sdx += dxu;
-                                sdx2 += dxu * dxu;
+                            for (int nbr = 0; nbr < 6; ++nbr) {
+                                if ((nbt.mask >> nbr) & 1u) {
+                                    const float dxu = th[i] - nv[nbr * nbt.stride];
+                                    sdx += dxu;
+                                    sdx2 += dxu * dxu;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int nbr = 0; nbr < 6; ++nbr) {
+                                const int u = e.neighbours[(int64_t)nbr * e.ld + w];
+                                if (u >= 0) {
+                                    const float dxu = th[i] - nbs[u];
+                                    sdx += dxu;
+                                    sdx2 += dxu * dxu;
+                                }
                             }
                         }
                         cost += lw * (-0.5f * lak + 0.25f * ak * sdx2);
@@ -275,7 +301,7 @@ struct VoxelStep {
         if (numeric) {
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                if (LEAN || e.prior_type[i] != SVBASL_PRIOR_MRF) {
+                if (!SPATIAL || e.prior_type[i] != SVBASL_PRIOR_MRF) {
                     const float q = a_hyp[i];                           // sum_s lw (theta-m)^2 / v
                     cost += 0.5f * q + (float)S * lw * 0.5f * plog[i];
                     a_hyp[i] = 0.5f * (q - (float)S * lw);              // sum_s lw/2 ((theta-m)^2/v - 1)

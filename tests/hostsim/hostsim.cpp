@@ -7,13 +7,16 @@
 
 #include "voxel_step.h"
 #include "model_aslrest.h"
+#include <vector>
 #include "model_nn.h"
 #include "model_disp.h"
 #include "model_list.h"
 
 using namespace svb;
 
-template <class M, int NBT, bool LEAN = false>
+// FL: flavour of VoxelStep (0 generic, 1 lean, 2 lean + spatial prior).  Flavour 2 also stages the neighbours'
+// samples of the first spatial parameter in an NbTile, as the CUDA kernel does in shared memory.
+template <class M, int NBT, int FL = 0>
 static int run_step(const svbasl_model *md, const svbasl_engine *e, const svbasl_adam *ad, int64_t step0, float *cost,
                     float *grad, double *cost_sum, double *ak_grad) {
     const int n_iters = ad ? ad->n_iters : 1;
@@ -21,12 +24,31 @@ static int run_step(const svbasl_model *md, const svbasl_engine *e, const svbasl
     const EngineConst ec = make_engine_const(*e);
     for (int64_t local = 0; local < e->n_vox; ++local) {
         const int64_t w = e->w_begin + local;
-        VoxelStep<M, NBT, LEAN> vs;
+        VoxelStep<M, NBT, FL> vs;
         vs.load(*e, w);
+        NbTile nbt = {nullptr, 0, -1, 0u};
+        std::vector<float> tile;
+        if (FL == 2) {
+            for (int i = 0; i < e->n_par && nbt.param < 0; ++i)
+                if (e->prior_type[i] == SVBASL_PRIOR_MRF) nbt.param = i;
+            if (nbt.param >= 0) {
+                const int S = e->n_samples;
+                tile.assign((size_t)6 * S, 0.0f);
+                const float *src = e->spatial_samples + (int64_t)ec.sp_slot[nbt.param] * S * e->ld;
+                for (int k = 0; k < 6; ++k) {
+                    const int u = e->neighbours[(int64_t)k * e->ld + w];
+                    if (u < 0) continue;
+                    nbt.mask |= 1u << k;
+                    for (int sidx = 0; sidx < S; ++sidx) tile[(size_t)sidx * 6 + k] = src[(int64_t)sidx * e->ld + u];
+                }
+                nbt.v = tile.data();
+                nbt.stride = 1;
+            }
+        }
         for (int it = 0; it < n_iters; ++it) {
             const int64_t step = (ad ? ad->step0 : step0) + it;
             const int row0 = (ad && ad->n_batches > 1) ? (int)(step % ad->n_batches) : e->t_row0;
-            float c = vs.elbo_grad(dm, *e, ec, w, step, row0);
+            float c = vs.elbo_grad(dm, *e, ec, w, step, row0, nbt);
             if (cost) cost[w] = c;
             if (grad) vs.store_grads(*e, grad, w);
             if (ad) {
@@ -109,7 +131,7 @@ extern "C" int hostsim_step(const svbasl_model *md, const svbasl_engine *e, cons
                             float *cost, float *grad, double *cost_sum, double *ak_grad, int nbt) {
     if (is_nn(md)) {
         if (nbt == 6) return run_step<AslNN, 6>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
-        if (nbt == 106) return run_step<AslNN, 6, true>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
+        if (nbt == 106) return run_step<AslNN, 6, 1>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
         return run_step<AslNN, 0>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
     }
     if (md->kind == SVBASL_MODEL_ASLREST_DISP) {
@@ -125,9 +147,10 @@ extern "C" int hostsim_step(const svbasl_model *md, const svbasl_engine *e, cons
         HOSTSIM_ASLREST_FLAGS
 #undef X
     }
-    // nbt = 100 + NBT selects the lean (production) flavour of the same layout
+    // nbt = 100 + NBT selects the lean (production) flavour of the same layout, 200 + NBT lean + spatial
 #define Y(F, NBT) if (md->kind == SVBASL_MODEL_ASLREST && f == F && nbt == NBT) return run_step<AslRest<F>, NBT>(md, e, ad, step, cost, grad, cost_sum, ak_grad); \
-    if (md->kind == SVBASL_MODEL_ASLREST && f == F && nbt == 100 + NBT) return run_step<AslRest<F>, NBT, true>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
+    if (md->kind == SVBASL_MODEL_ASLREST && f == F && nbt == 100 + NBT) return run_step<AslRest<F>, NBT, 1>(md, e, ad, step, cost, grad, cost_sum, ak_grad); \
+    if (md->kind == SVBASL_MODEL_ASLREST && f == F && nbt == 200 + NBT) return run_step<AslRest<F>, NBT, 2>(md, e, ad, step, cost, grad, cost_sum, ak_grad);
     HOSTSIM_FAST
 #undef Y
     return -2;
