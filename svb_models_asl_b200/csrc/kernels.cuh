@@ -201,11 +201,38 @@ static __global__ void __launch_bounds__(kBlock) spatial_sample_kernel(const __g
     const int64_t u = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (u >= a.n_local) return;
     const uint32_t key = rng_key(a.e.seed, a.e.step_dev ? (int64_t)*a.e.step_dev : a.step);
-    for (int p = 0; p < a.e.n_par; ++p) {
+    const int S = a.e.n_samples, n = a.e.n_par;
+    const int64_t ld = a.e.ld;
+    int p_first = 0;
+    if (!a.e.eps) {
+        // Parameters 0 and 1 (ftiss, delttiss: the usual spatial ones) depend on the first pair of draws only:
+        // one Philox call per sample serves both, the row of L is read once (same arithmetic as sample_theta).
+        const int s0 = a.ec.sp_slot[0], s1 = n > 1 ? a.ec.sp_slot[1] : -1;
+        p_first = n > 1 ? 2 : 1;
+        if (s0 >= 0 || s1 >= 0) {
+            const float *st = a.e.state + u;
+            const float mu0 = st[0], sd0 = fexp(0.5f * st[(int64_t)n * ld]);
+            float mu1 = 0.0f, sd1 = 0.0f, od10 = 0.0f;
+            if (s1 >= 0) {
+                mu1 = st[ld];
+                sd1 = fexp(0.5f * st[(int64_t)(n + 1) * ld]);
+                od10 = st[(int64_t)(2 * n + stri(1, 0)) * ld];
+            }
+            float *o0 = a.out + (int64_t)(s0 >= 0 ? s0 : 0) * S * ld + u;
+            float *o1 = a.out + (int64_t)(s1 >= 0 ? s1 : 0) * S * ld + u;
+            for (int s = 0; s < S; ++s) {
+                float e0, e1;
+                normal2(key, a.e.vox_offset + u, s, 0, e0, e1);
+                if (s0 >= 0) o0[(int64_t)s * ld] = mu0 + sd0 * e0;
+                if (s1 >= 0) o1[(int64_t)s * ld] = (mu1 + od10 * e0) + sd1 * e1;
+            }
+        }
+    }
+    for (int p = p_first; p < n; ++p) {
         const int slot = a.ec.sp_slot[p];
         if (slot < 0) continue;
-        for (int s = 0; s < a.e.n_samples; ++s)
-            a.out[((int64_t)slot * a.e.n_samples + s) * a.e.ld + u] = sample_theta(a.e, key, u, p, s);
+        for (int s = 0; s < S; ++s)
+            a.out[((int64_t)slot * S + s) * ld + u] = sample_theta(a.e, key, u, p, s);
     }
 }
 
