@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--cpu-voxels", type=int, default=100_000, help="voxels of the bounded CPU sample")
     ap.add_argument("--cpu-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo-mode", default="peer", choices=["peer", "peer+nccl", "nccl"],
+                    help="spatial workload on N > 1 GPUs: how halo state and the log-ak gradient travel")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, out)
@@ -239,7 +241,7 @@ def main():
         fit.lo, fit.hi = 0, W                                           # every rank owns its own W voxels (weak scaling)
     fit._setup(model.tpts(), dm.data_flattened, wl["batch"], FIT_OPTIONS["sample_size"], FIT_OPTIONS["learning_rate"],
                epochs=4 * (K + WU) + 64, force_num_latent_loss=FIT_OPTIONS["force_num_latent_loss"],
-               **{k: v for k, v in model_opts.items() if k == "param_overrides"})
+               halo_mode=args.halo_mode, **{k: v for k, v in model_opts.items() if k == "param_overrides"})
     data_host = dm.data_flattened
     f = fit.fused
     f.n_vox_global = W if cube else W * world
@@ -333,14 +335,16 @@ def main():
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if cube else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"] + ", sample-based latent loss, Adam fused", "name": args.workload,
-                   "voxels_per_gpu": W, "n_state": n_state, "rng": "philox2x32-10 in-kernel",
+                   "voxels_per_gpu": W, "n_state": n_state,
+                   **({"halo_mode": args.halo_mode} if (f.mrf and world > 1) else {}), "rng": "philox2x32-10 in-kernel",
                    "l2": "working set %.0f MB per step > 126 MB L2 (no flush needed)" % (bytes_per_voxel * W / 1e6)},
         "clocks": clocks,
         "e2e": {"value": (W_total * K / e2e_s) if e2e_ok else None, "unit": "voxel-iters/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 8, "ms_per_step": e2e_s / K * 1e3,
                 "path": "svbasl_step_host: pinned host batch (data rows + the batch's TIs) -> H2D -> fused step -> "
                         "D2H cost, double-buffered"},
-        "gpu_launches": K,
+        # spatial iteration = pre-pass + step launch(es: interior + boundary slabs when sharded) + hyper step
+        "gpu_launches": K * (2 + len(getattr(f, "ranges", None) or [0])) if f.mrf else K,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "kernel": "step_kernel<%s, B=%d, lean>" % (wl["model"], f.B),
                      "algorithmic_bytes_per_voxel_iter": bytes_per_voxel, "avg_launch_ms": per_launch_ms,

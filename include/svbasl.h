@@ -219,6 +219,22 @@ int svbasl_hyper_step(float *log_ak, float *m, float *v, const double *ak_grad, 
  * ak_grad is zeroed for the next iteration and *step_dev += 1. */
 int svbasl_hyper_step_dev(float *log_ak, float *m, float *v, double *ak_grad, int32_t n, float grad_scale,
                           const float *lr_t, long long *step_dev, float beta1, float beta2, float epsilon, void *stream);
+/* The same tail for a spatial prior sharded over the GPUs of one box, with the all-reduce of ak_grad fused in and
+ * done over NVLink peer memory instead of a separate NCCL launch (replaces svb's session-wide reduction of the
+ * MRFSpatialPrior gradient + svbasl_hyper_step_dev): every rank stores its partial sums and a sequence number
+ * (= *step_dev + 1) into ITS slot of every rank's mailbox, waits until all `world` slots of its own mailbox carry
+ * that number, adds them in rank order (bit-identical on every rank) and applies the Adam step.  Because every
+ * rank's stores are ordered behind its step kernels, the wait is also the barrier that makes the neighbours'
+ * mirrored boundary state (svbasl_engine.peer_lo / peer_hi) visible before the next iteration.
+ * mailboxes: HOST array of `world` device pointers, entry r = rank r's mailbox (own: the local allocation, others:
+ * svbasl_shared_open of their handle), each svbasl_mailbox_bytes(world) bytes, zero-initialised.
+ * status: device int32, set to 1 if a peer did not arrive within ~10 s (the wait is bounded so that a lost rank
+ * cannot hang the box); once set, later calls do not wait.  world <= SVBASL_MAX_PEERS. */
+#define SVBASL_MAX_PEERS 16
+int64_t svbasl_mailbox_bytes(int32_t world);
+int svbasl_hyper_step_peers(float *log_ak, float *m, float *v, double *ak_grad, int32_t n, float grad_scale,
+                            const float *lr_t, long long *step_dev, float beta1, float beta2, float epsilon,
+                            int32_t rank, int32_t world, void *const *mailboxes, int32_t *status, void *stream);
 /* *step_dev += inc (tail of a captured iteration without spatial priors). */
 int svbasl_advance_step(long long *step_dev, long long inc, void *stream);
 

@@ -8,10 +8,12 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libsvbasl.so")
+# SVBASL_LIB: load another build of the same library (e.g. a tuning variant); default = the in-tree build
+LIB_PATH = os.environ.get("SVBASL_LIB") or os.path.join(HERE, "csrc", "libsvbasl.so")
 
 MAX_PAR = 10
 MAX_SPATIAL = 4
+MAX_PEERS = 16
 
 MODEL_ASLREST, MODEL_ASLREST_DISP, MODEL_ASLNN = 0, 1, 2
 F_CASL, F_INFERATT, F_INFERART, F_INCWM, F_INFERWM, F_INFERT1, F_ARTONLY, F_DISP_INFER, F_DISP_ASWRITTEN = (
@@ -90,6 +92,10 @@ _EXPORTS = {
                                     C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "svbasl_hyper_step_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p,
                                         C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "svbasl_mailbox_bytes": (C.c_int64, [C.c_int32]),
+    "svbasl_hyper_step_peers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p,
+                                          C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32,
+                                          C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "svbasl_shared_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "svbasl_shared_free": (C.c_int, [C.c_void_p]),
     "svbasl_shared_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

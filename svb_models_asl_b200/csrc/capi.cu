@@ -174,6 +174,59 @@ __global__ void hyper_step_dev_kernel(float *log_ak, float *m, float *v, double 
     if (k == 0) *step_dev = step + 1;
 }
 
+// Mailbox of one rank: [2 parities][world] slots; slot q of parity p is written by rank q only.
+struct MailSlot {
+    double val[SVBASL_MAX_SPATIAL];
+    unsigned long long seq;
+};
+struct PeerBoxes {
+    MailSlot *box[SVBASL_MAX_PEERS];
+};
+
+// all-reduce of ak_grad over peer memory + hyper_step_dev_kernel's tail.  One thread per rank.
+__global__ void hyper_step_peers_kernel(PeerBoxes pb, int rank, int world, float *log_ak, float *m, float *v,
+                                        double *ak_grad, int n, float grad_scale, const float *lr_t, long long *step_dev,
+                                        float b1, float b2, float eps, int *status) {
+    __shared__ double part[SVBASL_MAX_PEERS][SVBASL_MAX_SPATIAL];
+    const int r = threadIdx.x;
+    const long long step = *step_dev;
+    const unsigned long long seq = (unsigned long long)step + 1ull;
+    const int par = (int)(seq & 1ull);
+    if (r < world) {
+        MailSlot *dst = pb.box[r] + (size_t)par * world + rank;
+        for (int k = 0; k < n; ++k) ((volatile double *)dst->val)[k] = ak_grad[k];
+        __threadfence_system();                       // values (and this GPU's earlier peer stores) before the flag
+        *(volatile unsigned long long *)&dst->seq = seq;
+        const MailSlot *src = pb.box[rank] + (size_t)par * world + r;
+        const volatile unsigned long long *flag = &src->seq;
+        if (*(volatile int *)status == 0) {
+            const long long t0 = clock64();
+            while (*flag != seq) {
+                if (clock64() - t0 > 20000000000ll) {   // ~10 s at 1.9 GHz
+                    atomicExch(status, 1);
+                    break;
+                }
+            }
+        }
+        __threadfence_system();
+        for (int k = 0; k < n; ++k) part[r][k] = ((const volatile double *)src->val)[k];
+    }
+    __syncthreads();
+    if (r < n) {
+        double sum = 0.0;
+        for (int q = 0; q < world; ++q) sum += part[q][r];
+        const float g = (float)(sum * (double)grad_scale);
+        const float mm = b1 * m[r] + (1.0f - b1) * g;
+        const float vv = b2 * v[r] + (1.0f - b2) * g * g;
+        m[r] = mm;
+        v[r] = vv;
+        log_ak[r] -= lr_t[step] * mm / (sqrtf(vv) + eps);
+        ak_grad[r] = 0.0;
+    }
+    __syncthreads();
+    if (r == 0) *step_dev = step + 1;
+}
+
 __global__ void advance_step_kernel(long long *step_dev, long long inc) { *step_dev += inc; }
 
 __global__ void hyper_step_kernel(float *log_ak, float *m, float *v, const double *ak_grad, int n, float grad_scale,
@@ -370,6 +423,27 @@ int svbasl_hyper_step_dev(float *log_ak, float *m, float *v, double *ak_grad, in
     hyper_step_dev_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(log_ak, m, v, ak_grad, n, grad_scale, lr_t, step_dev, beta1,
                                                               beta2, epsilon);
     return check_launch("hyper_step_dev_kernel");
+}
+
+int64_t svbasl_mailbox_bytes(int32_t world) { return world > 0 ? (int64_t)sizeof(MailSlot) * 2 * world : 0; }
+
+int svbasl_hyper_step_peers(float *log_ak, float *m, float *v, double *ak_grad, int32_t n, float grad_scale,
+                            const float *lr_t, long long *step_dev, float beta1, float beta2, float epsilon,
+                            int32_t rank, int32_t world, void *const *mailboxes, int32_t *status, void *stream) {
+    if (!log_ak || !m || !v || !ak_grad || !lr_t || !step_dev || !mailboxes || !status || n < 1 || n > SVBASL_MAX_SPATIAL ||
+        world < 1 || world > SVBASL_MAX_PEERS || rank < 0 || rank >= world) {
+        set_error("bad hyper_step_peers arguments");
+        return SVBASL_E_INVALID;
+    }
+    PeerBoxes pb;
+    memset(&pb, 0, sizeof(pb));
+    for (int r = 0; r < world; ++r) {
+        if (!mailboxes[r]) { set_error("mailbox of rank %d is NULL", r); return SVBASL_E_INVALID; }
+        pb.box[r] = (MailSlot *)mailboxes[r];
+    }
+    hyper_step_peers_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pb, rank, world, log_ak, m, v, ak_grad, n, grad_scale, lr_t,
+                                                              step_dev, beta1, beta2, epsilon, status);
+    return check_launch("hyper_step_peers_kernel");
 }
 
 int svbasl_shared_alloc(int64_t bytes, void **dev_ptr, unsigned char handle[SVBASL_IPC_HANDLE_BYTES]) {

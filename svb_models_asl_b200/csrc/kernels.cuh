@@ -7,7 +7,10 @@
 
 namespace svb {
 
-constexpr int kBlock = 128;
+#ifndef SVB_KBLOCK
+#define SVB_KBLOCK 128
+#endif
+constexpr int kBlock = SVB_KBLOCK;               // voxels (threads) per CTA
 
 struct StepArgs {
     DevModel md;
@@ -92,7 +95,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // fewer for the wide posteriors (P' >= 6: the Cholesky factor and its gradient alone are P'(P'+1) registers).
 template <class M>
 constexpr int min_blocks() {
-    return M::kRegHeavy ? 3 : (M::P + 1 <= 5 ? 4 : (M::P + 1 <= 7 ? 3 : 2));
+    return (128 / kBlock) * (M::kRegHeavy ? 3 : (M::P + 1 <= 5 ? 4 : (M::P + 1 <= 7 ? 3 : 2)));
 }
 
 // FL != 0: production flavours - fused update, no per-voxel cost / gradient outputs (see VoxelStep)

@@ -355,11 +355,14 @@ class FusedSvb:
         return self.cost_hist[step:step + 1]
 
     # ---- spatial prior, CUDA-graph replay, halo "exchange" fused into the step kernel over NVLink peer memory ----
-    def share_state_with_neighbours(self, plan):
+    def share_state_with_neighbours(self, plan, ak_reduce="peer"):
         """Move both state buffers into IPC-exportable device memory and exchange the handles with the adjacent
         ranks (once, at set-up), so that the step kernel can store boundary voxels' new state directly into the
-        neighbours' halo columns over NVLink."""
+        neighbours' halo columns over NVLink.  ak_reduce "peer": every rank also exports a small mailbox that all
+        ranks open, and the per-iteration all-reduce of the log-ak gradient (+ barrier) runs over it inside the
+        hyper-step kernel (svbasl_hyper_step_peers); "nccl": that reduction stays an NCCL all-reduce."""
         import torch.distributed as td
+        self.ak_reduce = ak_reduce
         n_bytes = 4 * self.n_state * self.ld
         self._shared = []
         handles = []
@@ -376,8 +379,31 @@ class FusedSvb:
             handles.append(bytes(handle))
         self._buf_alt0 = self.state_alt
         mine = {"rank": plan.rank, "ld": self.ld, "offset": plan.global_offset, "handles": handles}
+        if ak_reduce == "peer":
+            if plan.world > L.MAX_PEERS:
+                raise ValueError("peer-memory reduction supports at most %d ranks" % L.MAX_PEERS)
+            ptr = C.c_void_p()
+            handle = (C.c_ubyte * 64)()
+            with torch.cuda.device(self.dev):
+                L.check(self.lib.svbasl_shared_alloc(self.lib.svbasl_mailbox_bytes(plan.world), C.byref(ptr), handle))
+            self._mailbox = ptr
+            mine["mailbox"] = bytes(handle)
+            self.peer_status = torch.zeros(1, device=self.dev, dtype=torch.int32)
         everyone = [None] * plan.world
         td.all_gather_object(everyone, mine)
+        if ak_reduce == "peer":
+            self._mail_ptrs = (C.c_void_p * plan.world)()
+            self._mail_opened = []
+            for r, info in enumerate(everyone):
+                if r == plan.rank:
+                    self._mail_ptrs[r] = self._mailbox.value
+                    continue
+                p = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(info["mailbox"])
+                with torch.cuda.device(self.dev):
+                    L.check(self.lib.svbasl_shared_open(buf, C.byref(p)))
+                self._mail_ptrs[r] = p.value
+                self._mail_opened.append(p.value)
         self.peers = {}
         for side, r in (("lo", plan.rank - 1), ("hi", plan.rank + 1)):
             if 0 <= r < plan.world:
@@ -430,6 +456,10 @@ class FusedSvb:
                 graphs.append(g)
         torch.cuda.current_stream().wait_stream(side)
         self.graphs = graphs
+        if self.peers is not None:
+            import torch.distributed as td
+            torch.cuda.synchronize()
+            td.barrier()                  # the peer-memory reduction waits with a time-out: start the ranks together
 
     def _record_iteration(self):
         e = self.engine_desc(row0=0)
@@ -470,6 +500,14 @@ class FusedSvb:
             cur.wait_event(ev_join)
         else:
             launch(*ranges[0])
+        if self.peers is not None and getattr(self, "ak_reduce", "nccl") == "peer":
+            # all-reduce of the log-ak gradient over the ranks' mailboxes (NVLink peer memory) + its Adam step
+            L.check(self.lib.svbasl_hyper_step_peers(
+                self.log_ak.data_ptr(), self.ak_m.data_ptr(), self.ak_v.data_ptr(), self.ak_grad.data_ptr(),
+                len(self.mrf), 1.0 / self.n_vox_global, self.lr_t.data_ptr(), self.step_dev.data_ptr(), self.b1, self.b2,
+                self.adam_eps, self.plan.rank, self.plan.world, self._mail_ptrs, self.peer_status.data_ptr(),
+                _stream_ptr()))
+            return
         if self.reduce_fn is not None:
             self.reduce_fn(self.ak_grad)
         L.check(self.lib.svbasl_hyper_step_dev(self.log_ak.data_ptr(), self.ak_m.data_ptr(), self.ak_v.data_ptr(),
@@ -484,9 +522,13 @@ class FusedSvb:
         torch.cuda.synchronize()
         self.graphs = None
         if self.peers is not None:
+            timed_out = getattr(self, "peer_status", None) is not None and int(self.peer_status.item()) != 0
             for p in self.peers.values():
                 for ptr in p["ptrs"]:
                     self.lib.svbasl_shared_close(C.c_void_p(ptr))
+            for ptr in getattr(self, "_mail_opened", []):
+                self.lib.svbasl_shared_close(C.c_void_p(ptr))
+            self._mail_opened = []
             self.peers = None
             if td.is_available() and td.is_initialized():
                 td.barrier()                       # every neighbour has closed its mapping of our buffers
@@ -496,6 +538,12 @@ class FusedSvb:
             for ptr, _view in keep:
                 self.lib.svbasl_shared_free(ptr)
             self._shared = []
+            if getattr(self, "_mailbox", None) is not None:
+                self.lib.svbasl_shared_free(self._mailbox)
+                self._mailbox = None
+            if timed_out:
+                raise L.SvbAslError("svbasl_hyper_step_peers: a rank did not arrive within the time-out; the "
+                                    "spatial-prior results of this run are invalid")
         torch.cuda.synchronize()
 
     def finish(self):
@@ -523,7 +571,10 @@ class FusedSvb:
         cost = torch.zeros(self.ld, device=self.dev)
         grad = torch.zeros(self.n_state, self.ld, device=self.dev)
         if self.mrf:
-            self.ak_grad.zero_()
+            # the log-ak gradient of this evaluation goes to a scratch accumulator: the running one must stay zero
+            # between iterations (the graph-replayed iteration zeroes it at its END, svbasl_hyper_step_dev)
+            self.ak_grad_eval = torch.zeros_like(self.ak_grad)
+            e.ak_grad = self.ak_grad_eval.data_ptr()
             self.sample_spatial(e, self.step_count if step is None else step)
         L.check(self.lib.svbasl_elbo_grad(C.byref(self.mdesc), C.byref(e), self.step_count if step is None else step,
                                           cost.data_ptr(), grad.data_ptr(), None, _stream_ptr()))

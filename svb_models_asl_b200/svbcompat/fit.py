@@ -101,11 +101,13 @@ class SvbFit(LogBase):
             self.fused.halo_exchange = plan.exchange_halo
             self.fused.reduce_fn = ShardPlan.allreduce_sum
             plan.exchange_halo(self.fused.state)
-            mode = kwargs.get("halo_mode", "peer")       # "peer": fused stores over NVLink + CUDA graph; "nccl"
+            # "peer": halo stores and the log-ak all-reduce over NVLink peer memory, iteration replayed as a CUDA
+            # graph; "peer+nccl": same, the all-reduce by NCCL; "nccl": send/recv halo exchange on a side stream
+            mode = kwargs.get("halo_mode", "peer")
             if mode == "none":
                 pass
-            elif mode == "peer":
-                self.fused.share_state_with_neighbours(plan)
+            elif mode in ("peer", "peer+nccl"):
+                self.fused.share_state_with_neighbours(plan, ak_reduce="peer" if mode == "peer" else "nccl")
                 self.fused.enable_graph()
             elif kwargs.get("overlap_halo", True):
                 self.fused.enable_overlap(plan)

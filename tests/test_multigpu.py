@@ -48,10 +48,12 @@ def _worker(rank, world, port, vol_path, out_dir, spatial, halo_mode):
     td.destroy_process_group()
 
 
-@pytest.mark.parametrize("spatial,halo_mode", [(False, "peer"), (True, "peer"), (True, "nccl")])
+@pytest.mark.parametrize("spatial,halo_mode", [(False, "peer"), (True, "peer"), (True, "peer+nccl"), (True, "nccl")])
 def test_two_gpus_reproduce_one_gpu(tmp_path, spatial, halo_mode):
     """halo_mode "peer": boundary state stored straight into the neighbour's halo over NVLink peer memory by the step
-    kernel, whole iteration replayed as a CUDA graph; "nccl": explicit send/recv exchange on a side stream."""
+    kernel and log-ak gradient all-reduced over peer-memory mailboxes (svbasl_hyper_step_peers), whole iteration
+    replayed as a CUDA graph; "peer+nccl": the same with an NCCL all-reduce; "nccl": explicit send/recv exchange on a
+    side stream."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from svb.main import run
