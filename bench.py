@@ -64,6 +64,17 @@ def synth_truth(n, seed):
     return np.stack([ftiss, delt, fblood, deltblood]).astype(np.float32), rng
 
 
+def measured_traffic(workload, n_vox):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per voxel of that capture), scaled to
+    this launch's voxel count; None when no capture exists for the workload."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    entry = json.load(open(path)).get(workload)
+    return None if not entry else entry["dram_bytes_per_voxel"] * n_vox
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -346,7 +357,8 @@ def main():
         # spatial iteration = pre-pass + step launch(es: interior + boundary slabs when sharded) + hyper step
         "gpu_launches": K * (2 + len(getattr(f, "ranges", None) or [0])) if f.mrf else K,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "step_kernel<%s, B=%d, lean>" % (wl["model"], f.B),
+                     "traffic": measured_traffic(args.workload, W), "peak_source": peak_src,
+                     "kernel": "step_kernel<%s, B=%d, %s>" % (wl["model"], f.B, "lean+spatial" if f.mrf else "lean"),
                      "algorithmic_bytes_per_voxel_iter": bytes_per_voxel, "avg_launch_ms": per_launch_ms,
                      "fp32": {"lane_instr_per_voxel_iter": lane_instr_per_voxel,
                               "achieved_tlane_per_s": lane_instr_per_voxel * W / (per_launch_ms * 1e-3) / 1e12,
