@@ -178,6 +178,69 @@ def run_reference(args, out):
 
 
 # ----------------------------------------------------------------------------------------------------
+def prefer_gpu_local_host_memory(dev_index):
+    """Best effort, Linux only: ask the kernel to place this process's NEW host pages (the pinned staging buffers
+    of the end-to-end leg) on the NUMA node the GPU hangs off, and run on that node's CPUs when the cpuset allows.
+    Returns a short description for the JSON line.  Never fatal.  Undone by restore_host_placement() once the
+    buffers exist (the CPU baseline must see every core)."""
+    global _SAVED_AFFINITY
+    _SAVED_AFFINITY = os.sched_getaffinity(0)
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(dev_index)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read())
+        if node < 0:
+            return "gpu numa node unknown"
+        note = "gpu %s on numa node %d" % (bdf, node)
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        if cpus & allowed:
+            os.sched_setaffinity(0, cpus & allowed)
+            note += ", cpus pinned to %d local" % len(cpus & allowed)
+        else:
+            note += ", no local cpu in cpuset"
+        mask = C.c_ulong(1 << node)
+        libc = C.CDLL(None, use_errno=True)
+        rc = libc.syscall(238, 1, C.byref(mask), C.c_ulong(8 * C.sizeof(C.c_ulong)))    # set_mempolicy(MPOL_PREFERRED)
+        note += ", mempolicy preferred" if rc == 0 else ", mempolicy refused (errno %d)" % C.get_errno()
+        return note
+    except Exception as exc:                                                       # noqa: BLE001
+        return "numa placement skipped: %s" % (str(exc)[:80],)
+
+
+_SAVED_AFFINITY = None
+
+
+def restore_host_placement():
+    try:
+        if _SAVED_AFFINITY:
+            os.sched_setaffinity(0, _SAVED_AFFINITY)
+        C.CDLL(None).syscall(238, 0, None, C.c_ulong(0))                           # MPOL_DEFAULT
+    except Exception:                                                              # noqa: BLE001
+        pass
+
+
+def h2d_copy_rate(h_buf, dev, n=20):
+    """Plain pinned-host -> device copy bandwidth of the end-to-end leg's own staging buffer (GB/s): the ceiling
+    of `e2e` on this box."""
+    import torch
+    d = torch.empty(h_buf.shape, dtype=h_buf.dtype, device=dev)
+    for _ in range(3):
+        d.copy_(h_buf, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        d.copy_(h_buf, non_blocking=True)
+    torch.cuda.synchronize()
+    return h_buf.numel() * h_buf.element_size() * n / (time.perf_counter() - t0) / 1e9
+
+
 def _claim_stdout():
     """Library chatter (e.g. NCCL's version banner) goes to stderr; stdout carries exactly ONE JSON line."""
     real = os.dup(1)
@@ -297,6 +360,7 @@ def main():
     # ---- end to end through the C ABI with HOST buffers (svb feeds each batch via feed_dict) ----
     from svb_models_asl_b200.ops import HostFeeder
     rows = list(range(0, f.T, f.n_batches))                           # the time points of batch 0
+    numa_note = prefer_gpu_local_host_memory(local_rank)
     h_data = torch.from_numpy(np.ascontiguousarray(data_host.T[rows])).pin_memory()    # [B, ld]
     # time points in the low-rank form the model defines them by (t = ti + z*slicedt, aslrest.py:438-440): the
     # batch's B inversion times travel with every step, the per-voxel slice offset is resident like the mask
@@ -310,7 +374,9 @@ def main():
         tp_full = np.broadcast_to(model.tpts(), data_host.shape)
         h_tpts = torch.from_numpy(np.ascontiguousarray(tp_full.T[rows])).pin_memory()
         h_ti = zoff_dev = None
+    restore_host_placement()
     e2e_ok = not f.mrf          # the host-staged entry point does not run the spatial pre-pass / hyper step
+    h2d_gbs = h2d_copy_rate(h_data, dev) if e2e_ok else None
     feeder = HostFeeder(f) if e2e_ok else None
     for i in range(WU if e2e_ok else 0):
         feeder.step(h_data, h_tpts, h_ti, zoff_dev)
@@ -352,6 +418,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": (W_total * K / e2e_s) if e2e_ok else None, "unit": "voxel-iters/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 8, "ms_per_step": e2e_s / K * 1e3,
+                "h2d_copy_gbs": h2d_gbs, "host_memory": numa_note,
                 "path": "svbasl_step_host: pinned host batch (data rows + the batch's TIs) -> H2D -> fused step -> "
                         "D2H cost, double-buffered"},
         # spatial iteration = pre-pass + step launch(es: interior + boundary slabs when sharded) + hyper step

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Attribute the executed warp-instructions of one kernel in an .ncu-rep to source lines and opcodes.
 
-    python profiles/attribute.py <report.ncu-rep> <object-or-cubin with -lineinfo> <mangled kernel name substring>
+    python profiles/attribute.py <report.ncu-rep> <object-or-cubin with -lineinfo> <mangled kernel name substring> \
+                                 [ncu kernel-name filter, e.g. regex:step_kernel, when the report holds several kernels]
 
 Joins ncu's SASS page (per-instruction `Instructions Executed`) with nvdisasm's line table of the same cubin.
 """
@@ -14,7 +15,7 @@ import tempfile
 import os
 
 
-def main(rep, obj, kernel):
+def main(rep, obj, kernel, name_filter=None):
     tmp = tempfile.mkdtemp()
     if obj.endswith(".o") or obj.endswith(".so"):
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, check=True, capture_output=True)
@@ -42,7 +43,8 @@ def main(rep, obj, kernel):
             break
     if not instrs:
         sys.exit("kernel not found in " + obj)
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    cmd = ["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-name", name_filter] if name_filter else [])
+    src = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
     hdr = rows[1]
     ia, ie = hdr.index("Address"), hdr.index("Instructions Executed")
@@ -91,4 +93,4 @@ def main(rep, obj, kernel):
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:4])
+    main(*sys.argv[1:5])
