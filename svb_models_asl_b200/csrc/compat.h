@@ -60,6 +60,21 @@ SVB_HD void async_copies_wait() {
 #endif
 }
 
+// Warp-level helpers for code with lane-dependent trip counts (model_disp.h).  Every lane of the warp that has not
+// exited the kernel must reach them (callers keep the surrounding control flow uniform).  No-ops on the host.
+SVB_HD void warp_converge() {
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+}
+SVB_HD int warp_max(int v) {
+#if defined(__CUDA_ARCH__)
+    return __reduce_max_sync(0xffffffffu, v);
+#else
+    return v;
+#endif
+}
+
 SVB_HD float fmin2(float a, float b) { return a < b ? a : b; }
 SVB_HD float fmax2(float a, float b) { return a > b ? a : b; }
 
