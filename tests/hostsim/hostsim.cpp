@@ -179,3 +179,16 @@ extern "C" void hostsim_fill_eps(float *eps, int64_t n_vox, int64_t ld, int64_t 
                 if (2 * k + 1 < n_par) eps[((int64_t)(2 * k + 1) * n_samples + s) * ld + w] = n1;
             }
 }
+
+// Q(a, x_k), dQ/da, dQ/dx along a sequence of arguments through the running evaluator (model_disp.h:
+// gamma_run_eval) and, for comparison, through the from-scratch igammac_d at every point.
+extern "C" void hostsim_gamma_run(float a, const float *xs, int n, float *q, float *dqa, float *dqx, float *q_ref,
+                                  float *dqa_ref, float *dqx_ref) {
+    const GammaConst g = gamma_const(a);
+    GammaRun r = gamma_run_start();
+    for (int k = 0; k < n; ++k) {
+        const float lnx = logf(fmaxf(xs[k], 1e-30f));
+        gamma_run_eval(g, r, xs[k], lnx, q[k], dqa[k], dqx[k]);
+        igammac_d(g, xs[k], lnx, q_ref[k], dqa_ref[k], dqx_ref[k]);
+    }
+}
