@@ -261,6 +261,9 @@ def main():
     ap.add_argument("--cpu-voxels", type=int, default=100_000, help="voxels of the bounded CPU sample")
     ap.add_argument("--cpu-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--iters-per-launch", type=int, default=8,
+                    help="additional measurement: this many iterations fused per launch (state, data and Adam "
+                         "moments stay on chip between them); 0 = skip")
     ap.add_argument("--halo-mode", default="peer", choices=["peer", "peer+nccl", "nccl"],
                     help="spatial workload on N > 1 GPUs: how halo state and the log-ak gradient travel")
     args = ap.parse_args()
@@ -314,7 +317,7 @@ def main():
     if not wl.get("cube"):
         fit.lo, fit.hi = 0, W                                           # every rank owns its own W voxels (weak scaling)
     fit._setup(model.tpts(), dm.data_flattened, wl["batch"], FIT_OPTIONS["sample_size"], FIT_OPTIONS["learning_rate"],
-               epochs=4 * (K + WU) + 64, force_num_latent_loss=FIT_OPTIONS["force_num_latent_loss"],
+               epochs=4 * (K + WU) + 64 + (K + 3) * max(0, args.iters_per_launch), force_num_latent_loss=FIT_OPTIONS["force_num_latent_loss"],
                halo_mode=args.halo_mode, **{k: v for k, v in model_opts.items() if k == "param_overrides"})
     data_host = dm.data_flattened
     f = fit.fused
@@ -356,6 +359,27 @@ def main():
     value = W_total * K / (total_ms * 1e-3)
     final_cost = float(f.cost_hist[f.step_count - 1].item()) / f.n_vox
     assert math.isfinite(final_cost), "non-finite cost"
+
+    # ---- the same iterations, several per launch (svbasl_adam.n_iters): nothing is re-read between them ----
+    fused = None
+    kf = min(args.iters_per_launch, f.max_fuse)
+    if kf > 1 and not f.mrf:
+        for _ in range(3):
+            f.step(kf)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            f.step(kf)
+        e1.record()
+        barrier()
+        tf_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            td.all_reduce(tf_ms, op=td.ReduceOp.MAX)
+        fused = {"iters_per_launch": kf, "launches": K, "value": W_total * K * kf / (float(tf_ms.item()) * 1e-3),
+                 "unit": "voxel-iters/s", "ms_per_iteration": float(tf_ms.item()) / (K * kf),
+                 "note": "same kernel, svbasl_adam.n_iters iterations per launch; not the headline value"}
+        assert math.isfinite(float(f.cost_hist[f.step_count - 1].item()))
 
     # ---- end to end through the C ABI with HOST buffers (svb feeds each batch via feed_dict) ----
     from svb_models_asl_b200.ops import HostFeeder
@@ -416,6 +440,7 @@ def main():
                    **({"halo_mode": args.halo_mode} if (f.mrf and world > 1) else {}), "rng": "philox2x32-10 in-kernel",
                    "l2": "working set %.0f MB per step > 126 MB L2 (no flush needed)" % (bytes_per_voxel * W / 1e6)},
         "clocks": clocks,
+        "fused": fused,
         "e2e": {"value": (W_total * K / e2e_s) if e2e_ok else None, "unit": "voxel-iters/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 8, "ms_per_step": e2e_s / K * 1e3,
                 "h2d_copy_gbs": h2d_gbs, "host_memory": numa_note,

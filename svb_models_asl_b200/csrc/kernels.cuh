@@ -167,13 +167,24 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
             if (!LEAN && a.grad) vs.store_grads(a.e, a.grad, w);
             if (update) {
                 if (vs.grads_finite() && cost == cost) {
-                    // iteration 0 reads the prefetched moments, later fused iterations re-read global memory
-                    if (it == 0) vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, it == n_iters - 1, m_sm, v_sm, kBlock);
-                    else vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, it == n_iters - 1, a.ad.m + w, a.ad.v + w, a.e.ld);
+                    // the moments live in the shared-memory tile they were prefetched into for the whole launch;
+                    // the last fused iteration writes them (and the state) back to global memory
+                    if (it == n_iters - 1)
+                        vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, true, m_sm, v_sm, kBlock, a.ad.m + w, a.ad.v + w, a.e.ld);
+                    else
+                        vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, false, m_sm, v_sm, kBlock, m_sm, v_sm, kBlock);
                     if (SPATIAL && it == n_iters - 1) vs.mirror_to_peers(a.e, w);
                 } else {
                     ++skipped;
-                    if (it == n_iters - 1) vs.store_state(a.e, w);
+                    if (it == n_iters - 1) {
+                        vs.store_state(a.e, w);
+                        if (n_iters > 1) {                     // moments of the earlier fused iterations
+                            for (int k = 0; k < n_state; ++k) {
+                                a.ad.m[(int64_t)k * a.e.ld + w] = m_sm[k * kBlock];
+                                a.ad.v[(int64_t)k * a.e.ld + w] = v_sm[k * kBlock];
+                            }
+                        }
+                    }
                     cost = 0.0f;
                 }
             }

@@ -394,32 +394,34 @@ struct VoxelStep {
     }
 
     // tf.train.AdamOptimizer step on this voxel's rows.  The old moments are read from (m_rd, v_rd) with row
-    // stride rd_stride - global memory, or the shared-memory tile the kernel prefetched them into - and the
-    // new ones written to global memory.  With write_state the new state is stored too.
+    // stride rd_stride and the new ones written to (m_wr, v_wr) with row stride wr_stride - global memory or the
+    // shared-memory tile the kernel prefetched them into (between the fused iterations of one launch the moments
+    // never leave shared memory).  With write_state the new state is stored too.
     SVB_HD void adam_update(const svbasl_engine &e, const svbasl_adam &ad, float lr_t, int64_t w, bool write_state,
-                            const float *m_rd, const float *v_rd, int64_t rd_stride) {
-        float *m = ad.m + w, *v = ad.v + w, *s = (e.state_out ? e.state_out : e.state) + w;
+                            const float *m_rd, const float *v_rd, int64_t rd_stride, float *m_wr, float *v_wr,
+                            int64_t wr_stride) {
+        float *s = (e.state_out ? e.state_out : e.state) + w;
         int a = 0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             float mm = m_rd[(int64_t)i * rd_stride], vv = v_rd[(int64_t)i * rd_stride];
             mu[i] = adam1(ad, lr_t, mu[i], g_mu[i], mm, vv);
-            int64_t o = (int64_t)i * e.ld;
-            m[o] = mm; v[o] = vv;
-            if (write_state) s[o] = mu[i];
+            m_wr[(int64_t)i * wr_stride] = mm;
+            v_wr[(int64_t)i * wr_stride] = vv;
+            if (write_state) s[(int64_t)i * e.ld] = mu[i];
             mm = m_rd[(int64_t)(N + i) * rd_stride]; vv = v_rd[(int64_t)(N + i) * rd_stride];
             lv[i] = adam1(ad, lr_t, lv[i], g_lv[i], mm, vv);
-            o = (int64_t)(N + i) * e.ld;
-            m[o] = mm; v[o] = vv;
-            if (write_state) s[o] = lv[i];
+            m_wr[(int64_t)(N + i) * wr_stride] = mm;
+            v_wr[(int64_t)(N + i) * wr_stride] = vv;
+            if (write_state) s[(int64_t)(N + i) * e.ld] = lv[i];
         }
 #pragma unroll
         for (int k = 0; k < NL; ++k) {
             float mm = m_rd[(int64_t)(2 * N + k) * rd_stride], vv = v_rd[(int64_t)(2 * N + k) * rd_stride];
             od[k] = adam1(ad, lr_t, od[k], g_od[k], mm, vv);
-            const int64_t o = (int64_t)(2 * N + k) * e.ld;
-            m[o] = mm; v[o] = vv;
-            if (write_state) s[o] = od[k];
+            m_wr[(int64_t)(2 * N + k) * wr_stride] = mm;
+            v_wr[(int64_t)(2 * N + k) * wr_stride] = vv;
+            if (write_state) s[(int64_t)(2 * N + k) * e.ld] = od[k];
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -427,9 +429,9 @@ struct VoxelStep {
                 const int row = 2 * N + NL + a++;
                 float mm = m_rd[(int64_t)row * rd_stride], vv = v_rd[(int64_t)row * rd_stride];
                 lphi[i] = adam1(ad, lr_t, lphi[i], g_lphi[i], mm, vv);
-                const int64_t o = (int64_t)row * e.ld;
-                m[o] = mm; v[o] = vv;
-                if (write_state) s[o] = lphi[i];
+                m_wr[(int64_t)row * wr_stride] = mm;
+                v_wr[(int64_t)row * wr_stride] = vv;
+                if (write_state) s[(int64_t)row * e.ld] = lphi[i];
             }
         }
     }

@@ -52,7 +52,7 @@ static int run_step(const svbasl_model *md, const svbasl_engine *e, const svbasl
             if (cost) cost[w] = c;
             if (grad) vs.store_grads(*e, grad, w);
             if (ad) {
-                if (vs.grads_finite() && c == c) vs.adam_update(*e, *ad, ad->lr_t[step], w, it == n_iters - 1, ad->m + w, ad->v + w, e->ld);
+                if (vs.grads_finite() && c == c) vs.adam_update(*e, *ad, ad->lr_t[step], w, it == n_iters - 1, ad->m + w, ad->v + w, e->ld, ad->m + w, ad->v + w, e->ld);
                 else { if (it == n_iters - 1) vs.store_state(*e, w); c = 0.0f; }
             }
             if (cost_sum) cost_sum[it] += c;

@@ -111,7 +111,7 @@ def test_fused_iterations_equal_single_iterations():
     rng = np.random.default_rng(3)
     vol, _f, _d = _sim_volume((4, 8, 9), rng, repeats=8, slicedt=0.0452)
     data = vol.reshape(-1, 48)
-    states = []
+    states, moments = [], []
     for fuse in (1, 8):
         dm = DataModel(data)
         model = AslRestModel(dm, tau=1.8, casl=True, plds=PLDS, repeats=[8], slicedt=0.0452, inferart=True)
@@ -119,13 +119,22 @@ def test_fused_iterations_equal_single_iterations():
         fit._setup(model.tpts(), dm.data_flattened, 6, 10, 0.01, epochs=8, force_num_latent_loss=True)
         f = fit.fused
         assert f.n_batches == 8 and f.B == 6
+        # after the posterior initialisation (which reads the data): non-finite samples in the device copy
+        f.data[3, 5] = float("nan")         # a voxel whose update is skipped in every iteration that sees row 3
+        f.data[7, 9] = float("nan")         # ... and one skipped in the LAST iteration of each fused launch
         for _ in range(16 // fuse):
             f.step(fuse)
         assert f.step_count == 16
         states.append(f.state.cpu().numpy())
+        moments.append((f.m.cpu().numpy(), f.v.cpu().numpy()))
         costs = f.cost_hist[:16].cpu().numpy()
         assert np.isfinite(costs).all() and (costs != 0).all()
+        assert int(f.nan_count.item()) == 4                    # 16 iterations over 8 strided batches: each row twice
     np.testing.assert_array_equal(states[0], states[1])
+    # the Adam moments stay in shared memory between fused iterations and must come back identical
+    np.testing.assert_array_equal(moments[0][0], moments[1][0])
+    np.testing.assert_array_equal(moments[0][1], moments[1][1])
+    assert np.isfinite(states[0]).all()
 
 
 def test_asl_example_real_data_options_on_synthetic_volume(tmp_path):
