@@ -161,7 +161,9 @@ typedef struct svbasl_adam {
     const float *lr_t;             /* device [>= step0 + n_iters] */
     float beta1, beta2, epsilon;
     int64_t step0;                 /* global index of the first iteration of this launch */
-    int32_t n_iters;               /* iterations fused into this launch (>1 only without spatial priors) */
+    int32_t n_iters;               /* iterations fused into this launch (>1 only without spatial priors): the state
+                                    * and the batch stay in registers, m / v in shared memory between them and are
+                                    * written back once; results are bit-identical to n_iters launches of one */
     int32_t n_batches;             /* time-point mini-batches per epoch: row0 = (step % n_batches) */
 } svbasl_adam;
 
