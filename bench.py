@@ -227,18 +227,20 @@ def restore_host_placement():
 
 
 def h2d_copy_rate(h_buf, dev, n=20):
-    """Plain pinned-host -> device copy bandwidth of the end-to-end leg's own staging buffer (GB/s): the ceiling
-    of `e2e` on this box."""
+    """Plain pinned-host -> device copy bandwidth of the end-to-end leg's own staging buffer (GB/s, CUDA events
+    around n back-to-back copies): what the PCIe link of this box gives `e2e`."""
     import torch
     d = torch.empty(h_buf.shape, dtype=h_buf.dtype, device=dev)
     for _ in range(3):
         d.copy_(h_buf, non_blocking=True)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(n):
         d.copy_(h_buf, non_blocking=True)
+    e1.record()
     torch.cuda.synchronize()
-    return h_buf.numel() * h_buf.element_size() * n / (time.perf_counter() - t0) / 1e9
+    return h_buf.numel() * h_buf.element_size() * n / (e0.elapsed_time(e1) * 1e-3) / 1e9
 
 
 def _claim_stdout():
