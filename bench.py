@@ -226,23 +226,6 @@ def restore_host_placement():
         pass
 
 
-def h2d_copy_rate(h_buf, dev, n=20):
-    """Plain pinned-host -> device copy bandwidth of the end-to-end leg's own staging buffer (GB/s, CUDA events
-    around n back-to-back copies): what the PCIe link of this box gives `e2e`."""
-    import torch
-    d = torch.empty(h_buf.shape, dtype=h_buf.dtype, device=dev)
-    for _ in range(3):
-        d.copy_(h_buf, non_blocking=True)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n):
-        d.copy_(h_buf, non_blocking=True)
-    e1.record()
-    torch.cuda.synchronize()
-    return h_buf.numel() * h_buf.element_size() * n / (e0.elapsed_time(e1) * 1e-3) / 1e9
-
-
 def _claim_stdout():
     """Library chatter (e.g. NCCL's version banner) goes to stderr; stdout carries exactly ONE JSON line."""
     real = os.dup(1)
@@ -402,7 +385,6 @@ def main():
         h_ti = zoff_dev = None
     restore_host_placement()
     e2e_ok = not f.mrf          # the host-staged entry point does not run the spatial pre-pass / hyper step
-    h2d_gbs = h2d_copy_rate(h_data, dev) if e2e_ok else None
     feeder = HostFeeder(f) if e2e_ok else None
     for i in range(WU if e2e_ok else 0):
         feeder.step(h_data, h_tpts, h_ti, zoff_dev)
@@ -445,7 +427,7 @@ def main():
         "fused": fused,
         "e2e": {"value": (W_total * K / e2e_s) if e2e_ok else None, "unit": "voxel-iters/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 8, "ms_per_step": e2e_s / K * 1e3,
-                "h2d_copy_gbs": h2d_gbs, "host_memory": numa_note,
+                "h2d_gbs_implied": (h2d * K / e2e_s / 1e9) if e2e_ok else None, "host_memory": numa_note,
                 "path": "svbasl_step_host: pinned host batch (data rows + the batch's TIs) -> H2D -> fused step -> "
                         "D2H cost, double-buffered"},
         # spatial iteration = pre-pass + step launch(es: interior + boundary slabs when sharded) + hyper step
