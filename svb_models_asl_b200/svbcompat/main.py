@@ -42,6 +42,10 @@ def run(data, model_name, output, mask=None, **kwargs):
     means, variances = svb.model_moments()              # [P', n_local]
     means, variances = svb.gather(means.T), svb.gather(variances.T)       # [W, P']
     fit = svb.gather(svb.model_fit()) if kwargs.get("save_model_fit", False) else None
+    final_cost = None
+    if kwargs.get("save_cost", False) and "voxel_cost" not in history:
+        # save_cost without save_cost_history: one evaluation of the per-voxel cost at the final posterior
+        final_cost = svb.gather(svb.full_cost().cpu().numpy())
     if svb.world > 1:
         for key in ("voxel_cost", "params"):
             if key in history:
@@ -68,6 +72,8 @@ def run(data, model_name, output, mask=None, **kwargs):
             save(history["params"][:, :, idx], "mean_%s_history" % param.name)
     if kwargs.get("save_cost", False) and "voxel_cost" in history:
         save(history["voxel_cost"][:, -1], "cost")
+    elif final_cost is not None:
+        save(final_cost, "cost")
     if kwargs.get("save_cost_history", False) and "voxel_cost" in history:
         save(history["voxel_cost"], "cost_history")
     if fit is not None:
