@@ -314,6 +314,11 @@ def main():
     lane_instr_per_voxel = {"sim_art": 60 * 50 + 10 * 60 + 300, "real_like": 60 * 21 + 10 * 30 + 200,
                             "spatial": 60 * 21 + 10 * 30 + 200, "nn": 60 * 420 + 10 * 30 + 200,
                             "disp": 120000}[args.workload]
+    # ... and algorithmic MUFU (XU-pipe) operations: 3 per element with the arterial term (1 without), 4 per
+    # (voxel, sample), 4 per Box-Muller pair of draws; aslnn: 40 per (voxel, sample, time point) row (20 tanh)
+    mufu_per_voxel = {"sim_art": 60 * 3 + 10 * 4 + 10 * 3 * 4, "real_like": 60 * 1 + 10 * 3 + 10 * 2 * 4,
+                      "spatial": 60 * 1 + 10 * 3 + 10 * 2 * 4, "nn": 60 * 40 + 10 * 3 + 10 * 2 * 4,
+                      "disp": None}[args.workload]
 
     def barrier():
         if world > 1:
@@ -443,6 +448,14 @@ def main():
                               "note": "FP32-pipe roofline 148 SM x 128 lanes x measured SM clock (SURVEY 8d)"}},
         "final_mean_cost": final_cost,
     }
+    if mufu_per_voxel:
+        xu_peak = 148 * 16 * sm_hz                             # MUFU: 16 lanes per SM per clock
+        xu_rate = mufu_per_voxel * W / (per_launch_ms * 1e-3)
+        line["roofline"]["xu"] = {"mufu_per_voxel_iter": mufu_per_voxel, "achieved_tops_per_s": xu_rate / 1e12,
+                                  "peak_tops_per_s": xu_peak / 1e12, "frac": xu_rate / xu_peak}
+        fracs = {"hbm": line["roofline"]["frac"], "fp32": line["roofline"]["fp32"]["frac"],
+                 "xu": line["roofline"]["xu"]["frac"]}
+        line["roofline"]["binding"] = max(fracs, key=fracs.get)
     if wl["model"] == "aslnn":
         # Model.evaluate of the surrogate: FP32-pipe kernel vs tcgen05 tensor-core kernel, 200k voxels x S x B rows
         from svb_models_asl_b200.ops import evaluate_model, nn_evaluate_tc
