@@ -157,3 +157,16 @@ def test_plugin_option_errors_match_the_reference_texts():
     assert model.tpts().shape[-1] == 12
     with pytest.raises(ValueError, match="time points"):
         cls(_dm(n=4, t=7), tau=1.8, plds=PLDS).tpts()
+
+
+def test_empty_shard_is_a_no_op(lib):
+    """n_vox == 0 (a rank that owns nothing): every entry point returns 0 without launching anything."""
+    m = _model(lib)
+    e = _engine(n_vox=0, ld=8)
+    assert lib.svbasl_elbo_grad(C.byref(m), C.byref(e), 0, None, None, None, None) == 0
+    ad = L.Adam()
+    ad.m = ad.v = ad.lr_t = 0x1000
+    ad.n_iters, ad.n_batches = 1, 1
+    ad.beta1, ad.beta2, ad.epsilon = 0.9, 0.999, 1e-8
+    assert lib.svbasl_step(C.byref(m), C.byref(e), C.byref(ad), None, None, None) == 0
+    assert lib.svbasl_sample_spatial(C.byref(e), 0, 0, C.c_void_p(0x1000), None) == 0
