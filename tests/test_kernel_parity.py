@@ -6,6 +6,7 @@ the host build of the same device headers (`hostsim`; runs in the GPU-less conta
 caught before GPU time is spent).  Tolerances are BASELINE.json's: forward signals 1e-5 relative (to the
 peak |signal| of the case), cost and gradients 1e-4 relative in float32.
 """
+import ctypes as C
 import math
 import zlib
 
@@ -489,3 +490,26 @@ def test_spatial_production_flavour_equals_generic(be, mrf):
     np.testing.assert_allclose(out[1][0], out[0][0], rtol=2e-6, atol=2e-7)
     np.testing.assert_allclose(out[1][1], out[0][1], rtol=1e-5)
     np.testing.assert_allclose(out[1][2], out[0][2], rtol=1e-6)
+
+
+@pytest.mark.parametrize("casl", [True, False])
+def test_largest_layout_matches_oracle_on_the_host_build(casl):
+    """Every optional parameter at once - GM + WM tissue, both T1s, arterial: P = 8, P' = 9, n_state = 55, the
+    widest posterior the kernels are instantiated for (SVBASL_MAX_PAR = 10).  Host build of the device code only:
+    the GPU instantiation of this layout is exercised from round 2 on."""
+    be = H.Backend("hostsim")
+    rng = np.random.default_rng(77 + int(casl))
+    W = 48
+    cfg = om.AslConfig(tau=1.8, t1b=1.65, casl=casl, incwm=True, inferwm=True, infert1=True, inferart=True, pc=0.98,
+                       pvgm=rng.uniform(0.1, 0.45, W).astype(np.float32),
+                       pvwm=rng.uniform(0.1, 0.45, W).astype(np.float32))
+    spec = H.aslrest_spec(cfg)
+    assert spec.n_par == 9 and len(cfg.param_names()) == 8
+    prob = H.synth_problem(cfg, spec, W, rng)
+    eps = rng.normal(size=(spec.n_par, spec.n_samples, W)).astype(np.float32)
+    ocost, ograd, _gh, _ = H.oracle_cost_grad(spec, prob, eps)
+    m = be.model_desc(cfg)
+    assert be.lib.hostsim_n_params(C.byref(m)) == 8
+    e, _b = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], eps)
+    cost, grad, _ = be.elbo_grad(m, e, spec.n_state)
+    _check_grads(cost, grad, ocost, ograd, tol=2 * GRAD_TOL)
