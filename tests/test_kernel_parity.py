@@ -513,3 +513,26 @@ def test_largest_layout_matches_oracle_on_the_host_build(casl):
     e, _b = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], eps)
     cost, grad, _ = be.elbo_grad(m, e, spec.n_state)
     _check_grads(cost, grad, ocost, ograd, tol=2 * GRAD_TOL)
+
+
+def test_sharp_dispersion_kernel_approaches_the_undispersed_model():
+    """Physical sanity (the reference keeps `aif_nodisp` "only for testing", aslrest_disp.py:112-131):
+    with a very narrow gamma kernel (s large, sp small) the dispersion model tends to the plain Buxton curve of
+    aslrest, up to the O(h) error of the 0.1 s convolution grid.  Host build of the device code."""
+    be = H.Backend("hostsim")
+    W = 40
+    rng = np.random.default_rng(2)
+    f = rng.uniform(5, 20, (W, 1, 1))
+    d = rng.uniform(0.5, 1.6, (W, 1, 1))
+    t = np.repeat(np.asarray(H.TIS, dtype=np.float32).reshape(1, 1, -1), W, axis=0)
+    plain = be.evaluate(om.AslConfig(tau=1.8, t1b=1.65, casl=True), np.stack([f, d]).astype(np.float32), t, 1)
+    disp_cfg = om.AslConfig(tau=1.8, t1b=1.65, casl=True, disp=True)
+    errs = []
+    for s in (1.5, 400.0):
+        p = np.stack([f, d, np.full_like(f, s), np.full_like(f, 0.05)]).astype(np.float32)
+        out = be.evaluate(disp_cfg, p, t, 1)
+        errs.append(np.abs(out - plain).max() / np.abs(plain).max())
+    # narrow kernel (mean (1+sp)/s = 2.6 ms): what remains is the right-endpoint rule of the 0.1 s grid, ~h/(2 T1app)
+    assert errs[1] < 0.06, errs
+    # broad kernel (mean 0.7 s): a visibly different curve
+    assert errs[0] > 3 * errs[1], errs
