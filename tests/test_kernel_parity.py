@@ -578,3 +578,57 @@ def test_fit_recovers_ground_truth_on_noiseless_data_host_build():
     # bolus arrives after most of the six time points (delttiss ~ 2.5) pin the arrival time only loosely
     assert np.median(f_err) < 0.01 and np.quantile(f_err, 0.9) < 0.04 and f_err.max() < 0.15, np.sort(f_err)[-5:]
     assert np.median(d_err) < 0.015 and np.quantile(d_err, 0.9) < 0.05 and d_err.max() < 0.25, np.sort(d_err)[-5:]
+
+
+def test_size_independent_properties_at_the_benchmark_size(be):
+    """At BASELINE.json's headline size (1,000,000 voxels on the GPU; the same test body with 3,000 voxels on the
+    host build) the oracle is too slow to compare against, so the check is through properties that hold exactly:
+    (1) the forward model is linear in the perfusion parameters: evaluate(2 f) == 2 evaluate(f) exactly;
+    (2) cost and gradient of a voxel depend on nothing but that voxel and its GLOBAL index (counter-based draws):
+        one launch over all voxels == separate launches over two unequal shards, bit for bit;
+    (3) everything is finite and no voxel is left untouched."""
+    W = 1_000_000 if be.kind == "cuda" else 3_000
+    rng = np.random.default_rng(123)
+    cfg = om.AslConfig(tau=1.8, t1b=1.65, casl=True, inferart=True)
+    spec = H.aslrest_spec(cfg)
+    # (1) linearity
+    f = rng.uniform(1, 20, (W, 1, 1))
+    d = rng.uniform(0.6, 2.5, (W, 1, 1))
+    fb = rng.uniform(0, 10, (W, 1, 1))
+    db = np.maximum(d - 0.3, 0.05)
+    z = rng.integers(0, 24, W)
+    t = (np.asarray(H.TIS)[None, :] + (z * 0.0452)[:, None]).astype(np.float32).reshape(W, 1, -1)
+    one = be.evaluate(cfg, np.stack([f, d, fb, db]).astype(np.float32), t, 1)
+    two = be.evaluate(cfg, np.stack([2 * f.astype(np.float32), d, 2 * fb.astype(np.float32), db]).astype(np.float32), t, 1)
+    assert np.isfinite(one).all() and (np.abs(one).max(axis=(1, 2)) > 0).all()
+    # bit for bit for every representable result; the GPU build flushes denormals (--ftz=true), so a product that
+    # lands below 1.2e-38 in one run and above it in the other may differ by that much - hence the 1e-30, which is
+    # 15 orders of magnitude below one ulp of any value the model produces for real inputs
+    np.testing.assert_allclose(two, 2.0 * one, rtol=0, atol=1e-30)
+    # (2) sharding invariance of the fused ELBO + gradient with in-kernel draws
+    n = spec.n_par
+    names = cfg.param_names()
+    state = np.zeros((spec.n_state, W), dtype=np.float32)
+    for i, col in enumerate((f, d, fb, db)):
+        state[i] = col[:, 0, 0] + rng.normal(0, 0.2, W)
+    state[n - 1] = rng.normal(0.3, 0.3, W)
+    state[n:2 * n] = rng.normal(-2.0, 0.3, (n, W))
+    state[2 * n:2 * n + spec.n_offdiag] = rng.normal(0, 0.05, (spec.n_offdiag, W))
+    state[2 * n + spec.n_offdiag:] = -3.0
+    assert len(names) == 4 and state.shape[0] == spec.n_state
+    data = (one[:, 0, :].T + rng.normal(0, 1.0, (6, W))).astype(np.float32)
+    tpts = np.ascontiguousarray(t[:, 0, :].T)
+    m = be.model_desc(cfg)
+    e, _b = be.engine_desc(spec, state, data, tpts, None, seed=17)
+    cost, grad, _ = be.elbo_grad(m, e, spec.n_state, step=5, nbt=6)
+    assert np.isfinite(cost).all() and np.isfinite(grad).all() and (cost != 0).all()
+    cut = (2 * W) // 5 + 1
+    parts_c, parts_g = np.zeros_like(cost), np.zeros_like(grad)
+    for w0, nv in ((0, cut), (cut, W - cut)):
+        es, _bs = be.engine_desc(spec, state, data, tpts, None, seed=17, w_begin=w0, n_vox=nv, n_vox_global=W)
+        c, g, _ = be.elbo_grad(m, es, spec.n_state, step=5, nbt=6)
+        assert (c[:w0] == 0).all() and (c[w0 + nv:] == 0).all()          # a launch writes its own range only
+        parts_c[w0:w0 + nv] = c[w0:w0 + nv]
+        parts_g[:, w0:w0 + nv] = g[:, w0:w0 + nv]
+    np.testing.assert_array_equal(parts_c, cost)
+    np.testing.assert_array_equal(parts_g, grad)
