@@ -52,7 +52,7 @@ extern "C" {
 #define SVBASL_F_INFERATT 0x02     /* inferatt: delttiss (/deltwm/deltblood) are parameters */
 #define SVBASL_F_INFERART 0x04     /* inferart: fblood (+deltblood) */
 #define SVBASL_F_INCWM 0x08        /* incwm: add a WM tissue component */
-#define SVBASL_F_INFERWM 0x10      /* inferwm: fwm (+deltwm) are parameters (implies INCWM) */
+#define SVBASL_F_INFERWM 0x10      /* inferwm: fwm (+deltwm, t1wm) are parameters; the WM SIGNAL needs INCWM (aslrest.py:327) */
 #define SVBASL_F_INFERT1 0x20      /* infert1: t1 (+t1wm) are parameters */
 #define SVBASL_F_ARTONLY 0x40      /* artonly: no tissue component */
 #define SVBASL_F_DISP_INFER 0x80   /* aslrest_disp infer_disp_params: s, sp are parameters */

@@ -31,7 +31,7 @@ static uint32_t canonical_flags(const svbasl_model *m) {
         f &= (SVBASL_F_CASL | SVBASL_F_INFERATT | SVBASL_F_INFERART | SVBASL_F_INCWM | SVBASL_F_INFERWM |
               SVBASL_F_INFERT1 | SVBASL_F_ARTONLY);
         if (f & SVBASL_F_ARTONLY) f |= SVBASL_F_INFERART;                      // aslrest.py:137-138
-        if (f & SVBASL_F_INFERWM) f |= SVBASL_F_INCWM;                        // aslrest.py:103-105
+        // inferwm does NOT imply incwm (only pvcorr sets both, aslrest.py:103-105): the layout keeps them apart
         if (f & SVBASL_F_ARTONLY) f &= ~(uint32_t)(SVBASL_F_INCWM | SVBASL_F_INFERWM);
     } else if (m->kind == SVBASL_MODEL_ASLREST_DISP) {
         f &= (SVBASL_F_CASL | SVBASL_F_INFERATT | SVBASL_F_INFERART | SVBASL_F_ARTONLY | SVBASL_F_DISP_INFER);

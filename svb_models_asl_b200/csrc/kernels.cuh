@@ -3,6 +3,7 @@
 // row segment per warp, and all per-sample work stays in registers.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include "voxel_step.h"
 
 namespace svb {
@@ -11,6 +12,7 @@ namespace svb {
 #define SVB_KBLOCK 128
 #endif
 constexpr int kBlock = SVB_KBLOCK;               // voxels (threads) per CTA
+constexpr int kMaxDevices = 64;                  // per-device caches of function attributes
 
 struct StepArgs {
     DevModel md;
@@ -178,6 +180,9 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
                     ++skipped;
                     if (it == n_iters - 1) {
                         vs.store_state(a.e, w);
+                        // the neighbour rank's halo column ping-pongs like our own buffers: it needs this
+                        // iteration's (unchanged) value too, or it keeps the one from two iterations ago
+                        if (SPATIAL) vs.mirror_to_peers(a.e, w);
                         if (n_iters > 1) {                     // moments of the earlier fused iterations
                             for (int k = 0; k < n_state; ++k) {
                                 a.ad.m[(int64_t)k * a.e.ld + w] = m_sm[k * kBlock];
@@ -306,14 +311,33 @@ int launch_step(const StepArgs &a0, cudaStream_t st) {
             if (a.e.prior_type[i] == SVBASL_PRIOR_MRF && (smem + tile + 1024) * min_blocks<M>() <= 227 * 1024) a.nb_param = i;
         if (a.nb_param >= 0) smem += tile;
     }
-    static size_t smem_allowed = 48 * 1024;                    // per instantiation
-    if (smem > smem_allowed) {
-        cudaError_t err = cudaFuncSetAttribute(step_kernel<M, NBT, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) {
-            set_error("step_kernel: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(err));
-            return SVBASL_E_CUDA;
+    // The opt-in above 48 KB is a per-device (per-context) function attribute.  It is raised ONCE per
+    // (instantiation, device) to everything the device can give this kernel, so that concurrent callers and
+    // processes driving several GPUs through the C ABI can never lower or skip it for one another.
+    if (smem > 48 * 1024) {
+        static std::atomic<int> smem_granted[kMaxDevices];       // bytes of dynamic shared memory opted in, 0 = not yet
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = -1;
+        int granted = dev >= 0 ? smem_granted[dev].load(std::memory_order_acquire) : 0;
+        if (granted == 0) {
+            int optin = 0;
+            cudaFuncAttributes fa;
+            cudaError_t err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev < 0 ? 0 : dev);
+            if (err == cudaSuccess) err = cudaFuncGetAttributes(&fa, step_kernel<M, NBT, FL>);
+            if (err == cudaSuccess) {
+                granted = optin - (int)fa.sharedSizeBytes;
+                err = cudaFuncSetAttribute(step_kernel<M, NBT, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, granted);
+            }
+            if (err != cudaSuccess) {
+                set_error("step_kernel: cannot opt in to large shared memory: %s", cudaGetErrorString(err));
+                return SVBASL_E_CUDA;
+            }
+            if (dev >= 0) smem_granted[dev].store(granted, std::memory_order_release);
         }
-        smem_allowed = smem;
+        if ((size_t)granted < smem) {
+            set_error("step_kernel needs %zu bytes of shared memory per CTA, the device grants %d", smem, granted);
+            return SVBASL_E_UNSUPPORTED;
+        }
     }
     step_kernel<M, NBT, FL><<<grid, kBlock, smem, st>>>(a);
     return check_launch("step_kernel");

@@ -44,7 +44,10 @@ struct AslRest {
     static constexpr bool ART = (F & (SVBASL_F_INFERART | SVBASL_F_ARTONLY)) != 0;
     static constexpr bool ARTONLY = (F & SVBASL_F_ARTONLY) != 0;
     static constexpr bool INFWM = (F & SVBASL_F_INFERWM) != 0 && !ARTONLY;
-    static constexpr bool INCWM = ((F & SVBASL_F_INCWM) != 0 || INFWM) && !ARTONLY;
+    // The WM signal is added only under incwm (aslrest.py:327); inferwm WITHOUT incwm (possible when pvcorr is
+    // not used, aslrest.py:103-105 sets both only under pvcorr) still creates the fwm / deltwm / t1wm parameters
+    // (aslrest.py:197-211,225-229) - they then have no effect on the prediction and only see their priors.
+    static constexpr bool INCWM = (F & SVBASL_F_INCWM) != 0 && !ARTONLY;
     static constexpr bool T1 = (F & SVBASL_F_INFERT1) != 0;
     static constexpr bool TISS = !ARTONLY;
 
@@ -223,8 +226,10 @@ struct AslRest {
                 if (INFWM) d[ix(I_FWM)] = Sw;
                 if (I_DELTWM >= 0) d[ix(I_DELTWM)] = ddw;
                 if (I_T1WM >= 0) d[ix(I_T1WM)] = dqw;
-            } else if (I_T1WM >= 0) {
-                d[ix(I_T1WM)] = 0.0f;
+            } else {
+                if (INFWM) d[ix(I_FWM)] = 0.0f;               // parameters without a signal term
+                if (I_DELTWM >= 0) d[ix(I_DELTWM)] = 0.0f;
+                if (I_T1WM >= 0) d[ix(I_T1WM)] = 0.0f;
             }
         } else {
             if (T1) d[ix(I_T1)] = 0.0f;                    // artonly + infert1: parameter exists, unused
@@ -255,8 +260,8 @@ struct AslRest {
             G[ix(I_FTISS)] *= s.gm.pv;
             if (ATT) G[ix(I_DELT)] *= s.gm.pvf;
             if (T1) G[ix(I_T1)] *= s.gm.pvf * s.gm.dqdt1;
-            if (INFWM) G[ix(I_FWM)] *= s.wm.pv;
-            if (I_DELTWM >= 0) G[ix(I_DELTWM)] *= s.wm.pvf;
+            if (INFWM && INCWM) G[ix(I_FWM)] *= s.wm.pv;
+            if (I_DELTWM >= 0 && INCWM) G[ix(I_DELTWM)] *= s.wm.pvf;
             if (I_T1WM >= 0 && INCWM) G[ix(I_T1WM)] *= s.wm.pvf * s.wm.dqdt1;
         }
         if (ART && I_DELTBLOOD >= 0) G[ix(I_DELTBLOOD)] *= s.fb;

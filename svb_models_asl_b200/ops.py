@@ -67,6 +67,37 @@ def evaluate_model(model, params, tpts):
     return out
 
 
+def device_init_stats(data, tpts=None):
+    """Per-voxel statistics of the data for the posterior initialisers (aslrest.py:461-520, svb's noise
+    initialiser), computed on the device by svbasl_init_stats: data [T, ld] CUDA tensor, tpts [T, ld] or None ->
+    dict(mean_t, max_t, var_t (population variance), t_at_max (time of the FIRST maximum, tf.argmax)), each [ld]."""
+    lib = _require_cuda()
+    T, ld = data.shape
+    outs = {k: torch.empty(ld, device=data.device, dtype=torch.float32) for k in ("mean_t", "max_t", "var_t", "t_at_max")}
+    if tpts is None:
+        outs["t_at_max"].zero_()
+    L.check(lib.svbasl_init_stats(data.data_ptr(), tpts.data_ptr() if tpts is not None else None, ld, ld, T,
+                                  outs["mean_t"].data_ptr(), outs["max_t"].data_ptr(), outs["var_t"].data_ptr(),
+                                  outs["t_at_max"].data_ptr(), _stream_ptr()))
+    return outs
+
+
+class InitData(np.ndarray):
+    """The `data` argument handed to a parameter's post_init(param, t, data) callback: the [W, T] host array the
+    reference's callbacks expect (aslrest.py:461-520), carrying `device_stats` - the per-voxel mean / max /
+    variance / time-of-maximum already reduced on the GPU - so that this package's own initialisers need not
+    reduce 10 M x 48 values on the host; a third-party callback sees a plain ndarray."""
+    device_stats = None
+
+    def __new__(cls, array, stats=None):
+        obj = np.asarray(array).view(cls)
+        obj.device_stats = stats
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.device_stats = getattr(obj, "device_stats", None) if obj is not None and getattr(obj, "shape", None) == self.shape else None
+
+
 _NN_TILES = {}
 
 
@@ -589,15 +620,12 @@ class FusedSvb:
         return out
 
     def init_stats(self):
-        """-> mean_t, max_t, var_t, t_at_max, each [ld] (posterior initialisers, aslrest.py:461-520)"""
-        outs = [torch.zeros(self.ld, device=self.dev) for _ in range(4)]
+        """-> dict(mean_t, max_t, var_t, t_at_max), each [ld] (posterior initialisers, aslrest.py:461-520)"""
         tp = self.tpts
         if tp is None:
             tp = self.ti[:, None] + (self.zoff[None, :] if self.zoff is not None else 0.0)
             tp = tp.expand(self.T, self.ld).contiguous()
-        L.check(self.lib.svbasl_init_stats(self.data.data_ptr(), tp.data_ptr(), self.ld, self.ld, self.T,
-                                           *[o.data_ptr() for o in outs], _stream_ptr()))
-        return outs
+        return device_init_stats(self.data, tp)
 
     def fill_eps(self, step):
         eps = torch.zeros(self.N, self.S, self.ld, device=self.dev)

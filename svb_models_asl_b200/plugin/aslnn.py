@@ -126,7 +126,9 @@ class AslNNModel(Model):
     def _init_flow(self, _param, _t, data):
         # aslnn.py:143-147 takes the plain mean; ftiss is LogNormal here, so a non-positive mean would make the
         # initial log-mean NaN - floored like aslrest's initialiser (aslrest.py:467)
-        return np.maximum(np.asarray(data).mean(axis=1), 0.1).astype(NP_DTYPE), None
+        st = getattr(data, "device_stats", None)               # reduced on the GPU by the engine (ops.InitData)
+        mean = np.asarray(st["mean_t"]) if st is not None else np.asarray(data).mean(axis=1)
+        return np.maximum(mean, 0.1).astype(NP_DTYPE), None
 
     # ---- weights: load / save / train ----
     def _init_nn(self):

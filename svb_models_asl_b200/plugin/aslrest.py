@@ -110,7 +110,7 @@ class AslRestModel(Model):
     def _resolve_inference_flags(self):
         if self.pvcorr:
             self.incwm = self.inferwm = True
-        self.incwm = bool(self.incwm or self.inferwm)
+        self.incwm = bool(self.incwm)        # inferwm alone adds the WM parameters but no WM signal (aslrest.py:327)
         if self.artonly:
             self.inferart = True
         self.inferart, self.infert1 = bool(self.inferart), bool(self.infert1)
@@ -233,23 +233,38 @@ class AslRestModel(Model):
         return "ASL resting state model: %s" % __version__
 
     # ---- posterior initialisers: f(param, t, data) -> (mean, var or None)  (aslrest.py:461-520) ----
+    # `data` is [n, T] for the n voxels being initialised (the engine passes its own shard).  When the engine has
+    # already reduced the data on the GPU (ops.InitData.device_stats, svbasl_init_stats) those statistics are used;
+    # with a plain array the reductions run in numpy, as in the reference.
+    @staticmethod
+    def _stat(data, key, fallback):
+        st = getattr(data, "device_stats", None)
+        return np.asarray(st[key], dtype=NP_DTYPE) if st is not None else fallback(np.asarray(data)).astype(NP_DTYPE)
+
+    def _shard_of(self, data, per_voxel):
+        """Per-voxel option arrays cover all nodes; the engine initialises one shard at a time."""
+        per_voxel = np.asarray(per_voxel, dtype=NP_DTYPE)
+        sl = getattr(data, "voxel_slice", None)
+        return per_voxel[sl] if (per_voxel.ndim and sl is not None) else per_voxel
+
     def _init_flow(self, _param, _t, data):
-        f = np.maximum(np.asarray(data).mean(-1).astype(NP_DTYPE), 0.1)
+        f = np.maximum(self._stat(data, "mean_t", lambda d: d.mean(-1)), 0.1)
         if not self.pvcorr:
             return f, None
         # PVEc: assume GM:WM perfusion 3:1 (aslrest.py:470-483)
-        fwm = f / (1 + 2 * np.asarray(self.pvgm, dtype=NP_DTYPE))
+        fwm = f / (1 + 2 * self._shard_of(data, self.pvgm))
         return (fwm if _param.name == "fwm" else 3 * fwm), None
 
     def _init_fblood(self, _param, _t, data):
-        return np.maximum(np.asarray(data).max(axis=1), 0.1).astype(NP_DTYPE), None
+        return np.maximum(self._stat(data, "max_t", lambda d: d.max(axis=1)), 0.1), None
 
     def _init_delt(self, _param, t, data):
-        n = self.data_model.n_nodes
+        n = len(data)
         if self.att_init == "max":
-            data, t = np.asarray(data), np.asarray(t)
-            idx = np.argmax(data, axis=1)
-            t_max = np.take_along_axis(np.broadcast_to(t, data.shape), idx[:, None], axis=1)[:, 0]
+            def host_t_at_max(d):
+                idx = np.argmax(d, axis=1)
+                return np.take_along_axis(np.broadcast_to(np.asarray(t), d.shape), idx[:, None], axis=1)[:, 0]
+            t_max = self._stat(data, "t_at_max", host_t_at_max)
             offset = 0.3 if _param.name == "fwm" else 0.0                # as written (never true for a delt)
             return (t_max + offset - self.tau).astype(NP_DTYPE), np.full(n, self.attsd, dtype=NP_DTYPE)
         # the reference returns attsd (a standard deviation) in the variance slot (aslrest.py:520)

@@ -18,7 +18,7 @@ import torch
 from . import dist as _dist
 from .parameter import Parameter
 from .utils import LogBase
-from ..ops import FusedSvb, device_array
+from ..ops import FusedSvb, InitData, device_array
 from ..sharding import ShardPlan, shard_bounds, world_info
 
 
@@ -26,7 +26,8 @@ def noise_parameter():
     """svb's NoiseParameter: prior LogNormal(1, 2e5), posterior LogNormal(1, 1.02), initialised from the
     per-voxel data variance floored at 1."""
     def _init(_param, _t, data):
-        var = np.asarray(data).var(axis=1)
+        st = getattr(data, "device_stats", None)
+        var = np.asarray(st["var_t"]) if st is not None else np.asarray(data).var(axis=1)
         return np.where(var < 1, 1.0, var).astype(np.float32), None
     return Parameter("noise", prior=_dist.LogNormal(1.0, 2e5), post=_dist.LogNormal(1.0, 1.02), post_init=_init)
 
@@ -82,20 +83,30 @@ class SvbFit(LogBase):
             n_vox_global=self.data_model.n_nodes, vox_offset=lo, halo=halo, neighbours=neighbours,
             ak_init=float(kwargs.get("ak", 1e-5)), ard_phi_max=kwargs.get("ard_phi_max", 1e6),
             latent_weight=float(kwargs.get("latent_weight", 1.0)), max_steps=epochs * n_batches + 1)
-        # initial posterior (svb: post_init(param, t, data) -> (mean, var) in MODEL space, mapped to internal)
+        # initial posterior (svb: post_init(param, t, data) -> (mean, var) in MODEL space, mapped to internal).
+        # Each rank initialises its own shard; the per-voxel reductions of the data (mean / max / variance / time of
+        # the maximum over time, aslrest.py:467,490,497-501) come from the device (svbasl_init_stats) and travel
+        # with the `data` argument (ops.InitData), so nothing of size [W, T] is reduced on the host.
+        own = slice(halo[0], halo[0] + (hi - lo))
+        stats = None
+        if kwargs.get("device_init", True):
+            stats = {k: v[own].cpu().numpy() for k, v in self.fused.init_stats().items()}
+        local_data = InitData(data[lo:hi], stats)
+        local_data.voxel_slice = slice(lo, hi)
+        local_t = tpts[lo:hi]
         means, variances = [], []
         for p in self.params:
             mean, var = None, None
             if p.post_init is not None:
-                mean, var = p.post_init(p, tpts, data)
+                mean, var = p.post_init(p, local_t, local_data)
                 if mean is not None:
                     mean = p.post_dist.transform.int_values(np.asarray(mean, dtype=np.float32))
             if mean is None:
-                mean = np.full(data.shape[0], np.mean(p.post_dist.mean), dtype=np.float32)
+                mean = np.full(hi - lo, np.mean(p.post_dist.mean), dtype=np.float32)
             if var is None:
-                var = np.full(data.shape[0], np.mean(p.post_dist.var), dtype=np.float32)
-            means.append(np.asarray(mean, dtype=np.float32)[lo:hi])
-            variances.append(np.asarray(var, dtype=np.float32)[lo:hi])
+                var = np.full(hi - lo, np.mean(p.post_dist.var), dtype=np.float32)
+            means.append(np.broadcast_to(np.asarray(mean, dtype=np.float32), (hi - lo,)))
+            variances.append(np.broadcast_to(np.asarray(var, dtype=np.float32), (hi - lo,)))
         self.fused.set_posterior(means, variances)
         if self.world > 1 and "M" in prior_types:
             self.fused.halo_exchange = plan.exchange_halo

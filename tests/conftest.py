@@ -40,3 +40,30 @@ def golden():
             tree.setdefault(case, {})[field] = blob[key]
         return tree
     return load
+
+
+_ERRORS = {}
+
+
+@pytest.fixture
+def record_error():
+    """Parity tests report the error they measured (not only pass/fail): record_error(name, key=value, ...).
+    Written at session end to gpurun_out/parity_errors_<tier>.json; the GPU tier's file is copied to profiles/."""
+    def rec(name, **values):
+        _ERRORS.setdefault(name, {}).update(values)
+    return rec
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _ERRORS:
+        return
+    import json
+    try:
+        import torch
+        tier = "gpu" if torch.cuda.is_available() else "cpu"
+    except Exception:  # noqa: BLE001
+        tier = "cpu"
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_errors_%s.json" % tier), "w") as f:
+        json.dump(_ERRORS, f, indent=1, sort_keys=True)

@@ -99,6 +99,9 @@ def aslrest_cases():
         # incwm without inferwm: the reference passes the float option `fwm` to tissue_signal,
         # which reads `.shape` from it (aslrest.py:292,328,352) -> AttributeError as shipped
         "casl_incwm_fixed": dict(casl=True, incwm=True, fwm=4.0, pvgm=0.6, pvwm=0.3, _expect_error=True),
+        # inferwm without incwm / pvcorr: fwm and deltwm are parameters (aslrest.py:197-211) but no WM signal is
+        # added (aslrest.py:327 tests incwm) and pc keeps its non-WM default 0.9 (aslrest.py:131-135)
+        "casl_inferwm_noinc": dict(casl=True, inferwm=True, inferart=True),
     }
     for name, opts in cases.items():
         opts = dict(opts)

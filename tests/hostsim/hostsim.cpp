@@ -81,7 +81,6 @@ static int run_eval(const svbasl_model *md, const float *params, const float *tp
 
 static uint32_t canon(uint32_t f) {
     if (f & SVBASL_F_ARTONLY) f |= SVBASL_F_INFERART;
-    if (f & SVBASL_F_INFERWM) f |= SVBASL_F_INCWM;
     if (f & SVBASL_F_ARTONLY) f &= ~(uint32_t)(SVBASL_F_INCWM | SVBASL_F_INFERWM);
     return f;
 }

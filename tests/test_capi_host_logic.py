@@ -27,14 +27,15 @@ def _dm(n=4, t=6):
 
 def _all_aslrest_options():
     for casl, att, art, t1 in itertools.product((False, True), repeat=4):
-        for wm in ({}, {"incwm": True, "pvgm": 0.6, "pvwm": 0.4}, {"incwm": True, "inferwm": True, "pvgm": 0.6, "pvwm": 0.4}):
+        for wm in ({}, {"incwm": True, "pvgm": 0.6, "pvwm": 0.4}, {"incwm": True, "inferwm": True, "pvgm": 0.6, "pvwm": 0.4},
+                   {"inferwm": True}):                 # WM parameters without a WM signal (aslrest.py:197-211 vs :327)
             yield dict(casl=casl, inferatt=att, inferart=art, infert1=t1, **wm)
     for casl, att in itertools.product((False, True), repeat=2):
         yield dict(casl=casl, inferatt=att, inferart=True, artonly=True)
 
 
 def test_every_aslrest_option_combination_has_a_kernel(lib):
-    """len(model.params) (aslrest.py:183-246) == P of the kernel the C ABI dispatches to, for all 52 layouts."""
+    """len(model.params) (aslrest.py:183-246) == P of the kernel the C ABI dispatches to, for all 68 layouts."""
     cls = get_model_class("aslrest")
     seen = set()
     for opts in _all_aslrest_options():
@@ -43,7 +44,7 @@ def test_every_aslrest_option_combination_has_a_kernel(lib):
         p = lib.svbasl_model_n_params(C.byref(m))
         assert p == len(model.params), (opts, p, [q.name for q in model.params])
         seen.add(m.flags)
-    assert len(seen) == 52
+    assert len(seen) == 68
 
 
 def test_every_disp_option_combination_has_a_kernel(lib):

@@ -284,3 +284,63 @@ def test_host_fed_steps_equal_device_resident_steps():
     np.testing.assert_array_equal(states[0], states[1])
     # ti + z*slicedt is formed in float32 on the device instead of float64-then-rounded on the host: 1 ulp in t
     np.testing.assert_allclose(states[2], states[0], rtol=2e-4, atol=2e-5)
+
+
+def test_device_initialisers_match_reference_goldens(golden):
+    """svbasl_init_stats (the per-voxel reductions behind _init_flow / _init_fblood / att_init="max",
+    aslrest.py:461-520) on the real-data sample of the golden fixture, through the plugin's own callbacks: the
+    device-reduced path (ops.InitData.device_stats, what SvbFit._setup hands to post_init) reproduces the values
+    the unmodified reference computed with numpy."""
+    from svb import DataModel
+    from svb_models_asl import AslRestModel
+    from svb_models_asl_b200.ops import InitData, device_array, device_init_stats
+    g = golden("aslrest_real")["real"]
+    data, tpts = g["data_sel"], g["tpts_sel"]                        # [343, 48] float32
+    dev = torch.device("cuda:0")
+    stats = device_init_stats(device_array(data.T.copy(), dev), device_array(tpts.T.copy(), dev))
+    stats = {k: v.cpu().numpy() for k, v in stats.items()}
+    np.testing.assert_allclose(stats["mean_t"], data.astype(np.float64).mean(1), rtol=2e-6, atol=2e-6)
+    np.testing.assert_array_equal(stats["max_t"], data.max(1))
+    np.testing.assert_allclose(stats["var_t"], data.astype(np.float64).var(1), rtol=1e-5)
+    np.testing.assert_array_equal(stats["t_at_max"], tpts[np.arange(len(data)), data.argmax(1)])
+    dm = DataModel(data)
+    init = InitData(data, stats)
+    for att_init, key_mean, key_var in (("", None, None), ("max", "init_delt_max_sel", "init_delt_max_var_sel")):
+        model = AslRestModel(dm, tau=1.8, casl=True, plds=PLDS, repeats=[8], slicedt=0.0452, inferart=True,
+                             att_init=att_init)
+        par = {p.name: p for p in model.params}
+        np.testing.assert_allclose(par["ftiss"].post_init(par["ftiss"], tpts, init)[0], g["init_ftiss_sel"], rtol=2e-6)
+        np.testing.assert_array_equal(par["fblood"].post_init(par["fblood"], tpts, init)[0], g["init_fblood_sel"])
+        mean, var = par["delttiss"].post_init(par["delttiss"], tpts, init)
+        if key_mean:
+            np.testing.assert_allclose(mean, g[key_mean], rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(var, g[key_var], rtol=1e-6)
+        else:
+            np.testing.assert_allclose(mean, float(g["init_delt"]), rtol=1e-6)
+            np.testing.assert_allclose(var, float(g["init_delt_var"]), rtol=1e-6)
+        # the host path (plain ndarray, as the reference passes it) gives the same initial posterior
+        np.testing.assert_allclose(par["ftiss"].post_init(par["ftiss"], tpts, data)[0], g["init_ftiss_sel"], rtol=2e-6)
+
+
+def test_nn_trainer_reduces_loss_and_round_trips_weights(tmp_path):
+    """AslNNModel's SGD trainer (aslnn.py:155-170, 262-299) on AslRestModel-simulated curves and the reference's
+    weights%i.npy / biases%i.npy layout (aslnn.py:326-340): a short run fits better than the initial network,
+    saves six files with the reference shapes and a fresh model loading them evaluates identically."""
+    from svb import DataModel
+    from svb_models_asl import AslNNModel
+    dm = DataModel(np.zeros((1, 6), dtype=np.float32))
+    opts = dict(tau=1.8, t1b=1.6, casl=True, repeats=1, t1=1.3, tis=[1.8 + p for p in PLDS])
+    model = AslNNModel(dm, train_examples=4000, train_steps=60, train_lr=0.05, train_batch_size=200,
+                       train_save=str(tmp_path / "w"), **opts)
+    x_train, x_test, y_train, y_test = model._get_training_data(4000, seed=3)
+    model._train_nn(x_train, y_train, 1, 0.05, 200)
+    mse0 = float(np.mean((model._ievaluate_nn(x_test) - y_test) ** 2))
+    model._train_nn(x_train, y_train, 60, 0.05, 200)
+    mse1 = float(np.mean((model._ievaluate_nn(x_test) - y_test) ** 2))
+    assert mse1 < 0.5 * mse0, (mse0, mse1)
+    model._save_nn(str(tmp_path / "w"))
+    shapes = [np.load(str(tmp_path / "w" / n)).shape for n in
+              ("weights0.npy", "biases0.npy", "weights1.npy", "biases1.npy", "weights2.npy", "biases2.npy")]
+    assert shapes == [(2, 10), (1, 10), (10, 10), (1, 10), (10, 1), (1, 1)]
+    again = AslNNModel(dm, train_load=str(tmp_path / "w"), **opts)
+    np.testing.assert_array_equal(again._ievaluate_nn(x_test), model._ievaluate_nn(x_test))

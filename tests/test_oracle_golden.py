@@ -159,3 +159,31 @@ def test_nn_matches_reference_source(golden):
     out = om.evaluate_nn(ws, bs, f, dl, torch.as_tensor(n["t"], dtype=torch.float64)).numpy()
     np.testing.assert_allclose(out, n["out64"], rtol=1e-12, atol=1e-13)
     np.testing.assert_allclose(n["tpts_default"], [TIS], rtol=1e-12)     # aslnn.py:139-141 (slicedt == 0)
+
+
+def test_committed_surrogate_weights_reproduce_the_analytic_curve():
+    """trained_data/ (the weights the aslnn scripts load; the reference does not ship its own)
+    against the analytic AslRestModel curve it was trained on (aslnn.py:191-199: t~U(1,5), delttiss~U(0.1,3),
+    ftiss = 1, CASL, t1b = 1.6): r^2 >= 0.999 like the report of aslnn.py:166-168 / gen_test_data.py:66-68."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    wdir = os.path.join(root, "trained_data")
+    ws = [np.load(os.path.join(wdir, "weights%i.npy" % i)) for i in range(3)]
+    bs = [np.load(os.path.join(wdir, "biases%i.npy" % i)) for i in range(3)]
+    assert [w.shape for w in ws] == [(2, 10), (10, 10), (10, 1)] and [b.shape for b in bs] == [(1, 10), (1, 10), (1, 1)]
+    rng = np.random.default_rng(99)
+    n = 20000
+    t = torch.as_tensor(rng.uniform(1.0, 5.0, n)).reshape(n, 1, 1)
+    d = torch.as_tensor(rng.uniform(0.1, 3.0, n)).reshape(n, 1, 1)
+    one = torch.ones_like(d)
+    cfg = om.AslConfig(casl=True, tau=1.8, t1b=1.6, t1=1.3)
+    y = om.evaluate(cfg, [one, d], t).numpy().ravel()
+    pred = om.evaluate_nn(ws, bs, one, d, t).numpy().ravel()
+    r2 = 1.0 - float(np.sum((y - pred) ** 2)) / float(np.sum((y - y.mean()) ** 2))
+    assert r2 >= 0.999, r2
+    # per-TI r^2 at the six inflow times of the example scripts (gen_test_data.py:66-68)
+    for ti in TIS:
+        tt = torch.full_like(d, ti)
+        yy = om.evaluate(cfg, [one, d], tt).numpy().ravel()
+        pp = om.evaluate_nn(ws, bs, one, d, tt).numpy().ravel()
+        assert 1.0 - float(np.sum((yy - pp) ** 2)) / float(np.sum((yy - yy.mean()) ** 2)) >= 0.995

@@ -24,6 +24,7 @@ CASES = {
     "pasl_t1_art": dict(casl=False, infert1=True, inferart=True),
     "casl_pvc": dict(casl=True, pvcorr=True, inferart=True),
     "casl_pvc_t1": dict(casl=True, pvcorr=True, infert1=True),
+    "casl_inferwm_noinc": dict(casl=True, inferwm=True, inferart=True),
 }
 
 
