@@ -389,7 +389,7 @@ def main():
         h_tpts = torch.from_numpy(np.ascontiguousarray(tp_full.T[rows])).pin_memory()
         h_ti = zoff_dev = None
     restore_host_placement()
-    e2e_ok = not f.mrf          # the host-staged entry point does not run the spatial pre-pass / hyper step
+    e2e_ok = not (f.mrf and world > 1 and args.halo_mode != "peer")   # host-fed spatial steps are one launch (peer mode)
     feeder = HostFeeder(f) if e2e_ok else None
     for i in range(WU if e2e_ok else 0):
         feeder.step(h_data, h_tpts, h_ti, zoff_dev)
@@ -436,7 +436,8 @@ def main():
                 "path": "svbasl_step_host: pinned host batch (data rows + the batch's TIs) -> H2D -> fused step -> "
                         "D2H cost, double-buffered"},
         # spatial iteration = pre-pass + step launch(es: interior + boundary slabs when sharded) + hyper step
-        "gpu_launches": K * (2 + len(getattr(f, "ranges", None) or [0])) if f.mrf else K,
+        # a spatial iteration is ONE launch too (fused tail); the NCCL modes add the hyper-step launch
+        "gpu_launches": K * (2 if (f.mrf and world > 1 and args.halo_mode != "peer") else 1),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": measured_traffic(args.workload, W), "peak_source": peak_src,
                      "kernel": "step_kernel<%s, B=%d, %s>" % (wl["model"], f.B, "lean+spatial" if f.mrf else "lean"),

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SVBASL_ABI_VERSION 1
+#define SVBASL_ABI_VERSION 2
 #define SVBASL_MAX_PAR 10          /* P' = model parameters + noise */
 #define SVBASL_MAX_SPATIAL 4
 #define SVBASL_NN_HIDDEN 10        /* aslnn.py:238-240: 2 -> 10 -> 10 -> 1 */
@@ -117,8 +117,9 @@ typedef struct svbasl_engine {
     /* posterior state [n_state][ld]: mean[P'], logvar[P'], offdiag[P'(P'-1)/2] rows (1,0),(2,0),(2,1),..,
      * then one log-phi row per ARD parameter */
     float *state;
-    float *state_out;              /* where the updated state is written; NULL = in place.  Must differ from
-                                      `state` when a spatial prior reads neighbours' state (ping-pong) */
+    float *state_out;              /* where the updated state is written; NULL = in place (a voxel only ever reads
+                                      its OWN state rows, also with spatial priors: neighbours are seen through
+                                      spatial_samples) */
     /* data / time points.  Row r of the batch is full-array row t_row0 + r*t_row_stride (svb's strided
      * time-point mini-batches).  tpts may be NULL: then t = ti[row] + zoff[w] (aslrest.py:438-440) */
     const float *data;             /* [T][ld] */
@@ -133,22 +134,34 @@ typedef struct svbasl_engine {
     /* spatial prior ("M"): neighbour table [6][ld] of LOCAL voxel indices, -1 = none.  The local arrays
      * cover a contiguous global range [lower halo | owned | upper halo]; halo voxels are only read.
      * spatial_samples [n spatial params][S][ld]: theta samples of the spatially-regularised parameters of every
-     * local voxel (halo included) for this step, written by svbasl_sample_spatial() before the step */
+     * local voxel (halo included) for THIS step: written by svbasl_sample_spatial() (first iteration, or whenever
+     * the state was set from outside) or by the previous fused step through spatial_samples_out. */
     const int32_t *neighbours;
     const float *spatial_samples;
+    /* Where a fused step (svbasl_step / svbasl_step_spatial) writes the samples of the NEXT iteration: after the Adam
+     * update each voxel draws theta(step+1) of its spatial parameters from its NEW state (the Philox stream of
+     * step+1) and stores them here, so that no pre-pass kernel runs between iterations.  Must be a different buffer
+     * from spatial_samples (other CTAs still read this step's samples): the caller ping-pongs two buffers.  NULL =
+     * do not write (svbasl_elbo_grad, or callers that run svbasl_sample_spatial before every step).  Needs the
+     * in-kernel draws (eps == NULL). */
+    float *spatial_samples_out;
     const float *log_ak;           /* [n spatial params] device */
     double *ak_grad;               /* [n spatial params] device accumulators: d(sum cost)/d(log ak) */
     /* Iteration index from DEVICE memory (CUDA-graph replay: a captured launch cannot change its arguments).
      * When non-NULL it replaces the `step` argument / adam->step0 everywhere (draws, lr_t index, batch rows) and
-     * `cost_sum` is then the BASE of a per-iteration history indexed by that counter.  svbasl_hyper_step_dev /
-     * svbasl_advance_step increment it at the end of an iteration. */
+     * `cost_sum` is then the BASE of a per-iteration history indexed by that counter.  svbasl_step_spatial (fused
+     * hyper step), svbasl_hyper_step_dev / svbasl_advance_step increment it at the end of an iteration. */
     const long long *step_dev;
-    /* Spatial prior across GPUs, fused communication: the updated state of the shard-boundary voxels is ALSO
-     * stored straight into the adjacent ranks' halo columns over NVLink peer memory (pointers obtained by CUDA IPC),
-     * so no separate halo exchange is launched.  peer_lo / peer_hi = the lower / upper neighbour's state_out buffer
-     * (row stride peer_*_ld); local index w is mirrored at peer index w + peer_*_shift when
-     * peer_*_first <= w < peer_*_first + peer_*_count (the owned voxels that lie in that neighbour's halo).  Visibility is ordered by the per-iteration all-reduce
-     * of ak_grad that every rank performs before its next iteration.  NULL = no mirroring. */
+    int32_t cost_sum_scalar;       /* non-zero: cost_sum stays a plain accumulator even with step_dev (svbasl_step_host) */
+    /* Spatial prior across GPUs, communication fused into the step kernel: a shard-boundary voxel stores its
+     * next-iteration samples ALSO into the adjacent rank's halo columns over NVLink peer memory (pointers obtained
+     * by CUDA IPC), so no halo exchange is launched and nothing but S floats per boundary voxel and spatial
+     * parameter crosses the link.  peer_lo / peer_hi = the lower / upper neighbour's buffer that plays the
+     * spatial_samples_out role in the same iteration (row stride peer_*_ld); local index w is mirrored at peer index
+     * w + peer_*_shift when peer_*_first <= w < peer_*_first + peer_*_count (the owned voxels that lie in that
+     * neighbour's halo; they must be the first / last owned voxels: the kernel processes them FIRST so that the
+     * stores are under way while the interior computes).  Visibility is ordered by the all-reduce of ak_grad that
+     * ends every iteration on every rank (svbasl_hyper: flags stored behind a system-scope fence).  NULL = none. */
     float *peer_lo, *peer_hi;
     int64_t peer_lo_ld, peer_hi_ld, peer_lo_shift, peer_hi_shift;
     int64_t peer_lo_first, peer_lo_count, peer_hi_first, peer_hi_count;
@@ -166,6 +179,25 @@ typedef struct svbasl_adam {
                                     * written back once; results are bit-identical to n_iters launches of one */
     int32_t n_batches;             /* time-point mini-batches per epoch: row0 = (step % n_batches) */
 } svbasl_adam;
+
+/* Tail of a spatial iteration fused into the step kernel (svbasl_step_spatial): the LAST CTA of the launch to
+ * finish (device counter `done_ctas`) all-reduces d(cost)/d(log ak) over the ranks' peer-memory mailboxes, applies
+ * the TF-Adam step to log ak, zeroes ak_grad and advances *step_dev - what svbasl_hyper_step_peers does as a
+ * separate launch.  With world == 1 no mailbox is touched.  The wait on the other ranks is bounded (~10 s); on
+ * expiry *status is set to 1 and later launches do not wait (the results are then invalid - poll status). */
+#define SVBASL_MAX_PEERS 16
+typedef struct svbasl_hyper {
+    float *log_ak;                 /* [n_spatial], the buffer engine->log_ak points to */
+    float *m, *v;                  /* [n_spatial] Adam moments of log ak */
+    const float *lr_t;             /* device table, indexed by the iteration */
+    long long *step_dev;           /* the counter engine->step_dev points to (required) */
+    unsigned int *done_ctas;       /* device counter, zero before the first launch; reset by the kernel */
+    float beta1, beta2, epsilon;
+    int32_t n_spatial;
+    int32_t rank, world;
+    void *mailboxes[SVBASL_MAX_PEERS]; /* entry r = rank r's mailbox (svbasl_mailbox_bytes(world) bytes, zeroed) */
+    int32_t *status;               /* device int32 */
+} svbasl_hyper;
 
 const char *svbasl_last_error(void);
 int svbasl_abi_version(void);
@@ -208,6 +240,14 @@ int svbasl_elbo_grad(const svbasl_model *model, const svbasl_engine *engine, int
 int svbasl_step(const svbasl_model *model, const svbasl_engine *engine, const svbasl_adam *adam,
                 double *cost_sum, long long *nan_count, void *stream);
 
+/* svbasl_step for spatial ("M") priors with the hyper-parameter tail fused in (svbasl_hyper above): ONE launch per
+ * iteration does sampling, model, likelihood, latent loss incl. the MRF term, gradients, Adam, the next iteration's
+ * neighbour samples (engine->spatial_samples_out, mirrored to the adjacent ranks through engine->peer_lo/hi), the
+ * all-reduce of d(cost)/d(log ak), its Adam step and the advance of the iteration counter.  hyper == NULL behaves
+ * like svbasl_step (the caller then reduces ak_grad and calls svbasl_hyper_step*). */
+int svbasl_step_spatial(const svbasl_model *model, const svbasl_engine *engine, const svbasl_adam *adam,
+                        const svbasl_hyper *hyper, double *cost_sum, long long *nan_count, void *stream);
+
 /* Pre-pass of a step with spatial priors: out [n spatial params][S][ld] = theta_{p,s} = mu_p + (L eps_s)_p for
  * every local voxel in [0, n_local) (owned + halo), from engine->state and the step's draws (engine->eps or the
  * Philox stream of `step`).  Neighbours then read each other's samples instead of rebuilding them. */
@@ -232,7 +272,6 @@ int svbasl_hyper_step_dev(float *log_ak, float *m, float *v, double *ak_grad, in
  * svbasl_shared_open of their handle), each svbasl_mailbox_bytes(world) bytes, zero-initialised.
  * status: device int32, set to 1 if a peer did not arrive within ~10 s (the wait is bounded so that a lost rank
  * cannot hang the box); once set, later calls do not wait.  world <= SVBASL_MAX_PEERS. */
-#define SVBASL_MAX_PEERS 16
 int64_t svbasl_mailbox_bytes(int32_t world);
 int svbasl_hyper_step_peers(float *log_ak, float *m, float *v, double *ak_grad, int32_t n, float grad_scale,
                             const float *lr_t, long long *step_dev, float beta1, float beta2, float epsilon,
@@ -273,7 +312,8 @@ typedef struct svbasl_host_ctx svbasl_host_ctx;
 int svbasl_host_ctx_create(svbasl_host_ctx **ctx, int64_t ld, int32_t n_batch);
 int svbasl_host_ctx_destroy(svbasl_host_ctx *ctx);
 int svbasl_step_host(svbasl_host_ctx *ctx, const svbasl_model *model, const svbasl_engine *engine,
-                     const svbasl_adam *adam, const float *host_data /*[B][ld]*/, const float *host_tpts /*[B][ld] or NULL*/,
+                     const svbasl_adam *adam, const svbasl_hyper *hyper /* spatial priors: fused tail, else NULL */,
+                     const float *host_data /*[B][ld]*/, const float *host_tpts /*[B][ld] or NULL*/,
                      const float *host_ti /*[B], used when host_tpts == NULL*/, double *host_cost_sum /* pinned, [1] */);
 int svbasl_host_sync(svbasl_host_ctx *ctx);
 

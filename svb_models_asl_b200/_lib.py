@@ -53,8 +53,9 @@ class Engine(C.Structure):
         ("data", C.c_void_p), ("tpts", C.c_void_p), ("ti", C.c_void_p), ("zoff", C.c_void_p),
         ("t_row0", C.c_int32), ("t_row_stride", C.c_int32),
         ("eps", C.c_void_p), ("seed", C.c_uint64),
-        ("neighbours", C.c_void_p), ("spatial_samples", C.c_void_p), ("log_ak", C.c_void_p), ("ak_grad", C.c_void_p),
-        ("step_dev", C.c_void_p),
+        ("neighbours", C.c_void_p), ("spatial_samples", C.c_void_p), ("spatial_samples_out", C.c_void_p),
+        ("log_ak", C.c_void_p), ("ak_grad", C.c_void_p),
+        ("step_dev", C.c_void_p), ("cost_sum_scalar", C.c_int32),
         ("peer_lo", C.c_void_p), ("peer_hi", C.c_void_p),
         ("peer_lo_ld", C.c_int64), ("peer_hi_ld", C.c_int64), ("peer_lo_shift", C.c_int64), ("peer_hi_shift", C.c_int64),
         ("peer_lo_first", C.c_int64), ("peer_lo_count", C.c_int64), ("peer_hi_first", C.c_int64), ("peer_hi_count", C.c_int64),
@@ -66,6 +67,16 @@ class Adam(C.Structure):
         ("m", C.c_void_p), ("v", C.c_void_p), ("lr_t", C.c_void_p),
         ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
         ("step0", C.c_int64), ("n_iters", C.c_int32), ("n_batches", C.c_int32),
+    ]
+
+
+class Hyper(C.Structure):
+    _fields_ = [
+        ("log_ak", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("lr_t", C.c_void_p), ("step_dev", C.c_void_p),
+        ("done_ctas", C.c_void_p),
+        ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
+        ("n_spatial", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+        ("mailboxes", C.c_void_p * MAX_PEERS), ("status", C.c_void_p),
     ]
 
 
@@ -87,6 +98,8 @@ _EXPORTS = {
                                    C.c_void_p, C.c_void_p]),
     "svbasl_step": (C.c_int, [C.POINTER(Model), C.POINTER(Engine), C.POINTER(Adam), C.c_void_p, C.c_void_p,
                               C.c_void_p]),
+    "svbasl_step_spatial": (C.c_int, [C.POINTER(Model), C.POINTER(Engine), C.POINTER(Adam), C.POINTER(Hyper), C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
     "svbasl_sample_spatial": (C.c_int, [C.POINTER(Engine), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "svbasl_hyper_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
                                     C.c_float, C.c_float, C.c_float, C.c_void_p]),
@@ -108,8 +121,8 @@ _EXPORTS = {
     "svbasl_model_fit": (C.c_int, [C.POINTER(Model), C.POINTER(Engine), C.c_void_p, C.c_void_p]),
     "svbasl_host_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int32]),
     "svbasl_host_ctx_destroy": (C.c_int, [C.c_void_p]),
-    "svbasl_step_host": (C.c_int, [C.c_void_p, C.POINTER(Model), C.POINTER(Engine), C.POINTER(Adam), C.c_void_p,
-                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "svbasl_step_host": (C.c_int, [C.c_void_p, C.POINTER(Model), C.POINTER(Engine), C.POINTER(Adam), C.POINTER(Hyper),
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "svbasl_host_sync": (C.c_int, [C.c_void_p]),
 }
 
@@ -137,7 +150,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.svbasl_abi_version() != 1:
+    if lib.svbasl_abi_version() != 2:
         raise SvbAslError("libsvbasl.so ABI version mismatch")
     _lib = lib
     return lib

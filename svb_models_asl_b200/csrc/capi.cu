@@ -174,57 +174,10 @@ __global__ void hyper_step_dev_kernel(float *log_ak, float *m, float *v, double 
     if (k == 0) *step_dev = step + 1;
 }
 
-// Mailbox of one rank: [2 parities][world] slots; slot q of parity p is written by rank q only.
-struct MailSlot {
-    double val[SVBASL_MAX_SPATIAL];
-    unsigned long long seq;
-};
-struct PeerBoxes {
-    MailSlot *box[SVBASL_MAX_PEERS];
-};
-
-// all-reduce of ak_grad over peer memory + hyper_step_dev_kernel's tail.  One thread per rank.
-__global__ void hyper_step_peers_kernel(PeerBoxes pb, int rank, int world, float *log_ak, float *m, float *v,
-                                        double *ak_grad, int n, float grad_scale, const float *lr_t, long long *step_dev,
-                                        float b1, float b2, float eps, int *status) {
+// svbasl_hyper_step_peers as a launch of its own (halo_mode "peer" without the fused tail): one CTA, hyper_tail
+__global__ void hyper_step_peers_kernel(svbasl_hyper hy, double *ak_grad, float grad_scale) {
     __shared__ double part[SVBASL_MAX_PEERS][SVBASL_MAX_SPATIAL];
-    const int r = threadIdx.x;
-    const long long step = *step_dev;
-    const unsigned long long seq = (unsigned long long)step + 1ull;
-    const int par = (int)(seq & 1ull);
-    if (r < world) {
-        MailSlot *dst = pb.box[r] + (size_t)par * world + rank;
-        for (int k = 0; k < n; ++k) ((volatile double *)dst->val)[k] = ak_grad[k];
-        __threadfence_system();                       // values (and this GPU's earlier peer stores) before the flag
-        *(volatile unsigned long long *)&dst->seq = seq;
-        const MailSlot *src = pb.box[rank] + (size_t)par * world + r;
-        const volatile unsigned long long *flag = &src->seq;
-        if (*(volatile int *)status == 0) {
-            const long long t0 = clock64();
-            while (*flag != seq) {
-                if (clock64() - t0 > 20000000000ll) {   // ~10 s at 1.9 GHz
-                    atomicExch(status, 1);
-                    break;
-                }
-            }
-        }
-        __threadfence_system();
-        for (int k = 0; k < n; ++k) part[r][k] = ((const volatile double *)src->val)[k];
-    }
-    __syncthreads();
-    if (r < n) {
-        double sum = 0.0;
-        for (int q = 0; q < world; ++q) sum += part[q][r];
-        const float g = (float)(sum * (double)grad_scale);
-        const float mm = b1 * m[r] + (1.0f - b1) * g;
-        const float vv = b2 * v[r] + (1.0f - b2) * g * g;
-        m[r] = mm;
-        v[r] = vv;
-        log_ak[r] -= lr_t[step] * mm / (sqrtf(vv) + eps);
-        ak_grad[r] = 0.0;
-    }
-    __syncthreads();
-    if (r == 0) *step_dev = step + 1;
+    hyper_tail(hy, ak_grad, grad_scale, part);
 }
 
 __global__ void advance_step_kernel(long long *step_dev, long long inc) { *step_dev += inc; }
@@ -343,7 +296,8 @@ int svbasl_nn_evaluate_tc(const svbasl_model *model, const float *b_tile, const 
 }
 
 static int run_step(const svbasl_model *model, const svbasl_engine *engine, const svbasl_adam *adam, int64_t step,
-                    float *cost, float *grad, double *cost_sum, long long *nan_count, void *stream) {
+                    float *cost, float *grad, double *cost_sum, long long *nan_count, void *stream,
+                    const svbasl_hyper *hyper = nullptr) {
     const KernelEntry *k = nullptr;
     int rc = validate(model, engine, &k, adam != nullptr && !cost && !grad);
     if (rc) return rc;
@@ -364,12 +318,41 @@ static int run_step(const svbasl_model *model, const svbasl_engine *engine, cons
             set_error("bad adam descriptor");
             return SVBASL_E_INVALID;
         }
-        if (mrf_mask(engine) && (adam->n_iters != 1 || !engine->state_out || engine->state_out == engine->state)) {
-            set_error("spatial priors need n_iters == 1 and a separate state_out (neighbours read the old state)");
+        if (mrf_mask(engine) && adam->n_iters != 1) {
+            set_error("spatial priors couple neighbouring voxels: n_iters must be 1");
             return SVBASL_E_INVALID;
         }
         a.ad = *adam;
         step = adam->step0;
+    }
+    if (engine->spatial_samples_out) {
+        if (!adam || !mrf_mask(engine) || engine->eps || engine->spatial_samples_out == engine->spatial_samples) {
+            set_error("spatial_samples_out needs a fused update with a spatial prior, in-kernel draws (eps == NULL) and a "
+                      "buffer different from spatial_samples");
+            return SVBASL_E_INVALID;
+        }
+    }
+    if (engine->peer_lo || engine->peer_hi) {
+        const int64_t nlo = engine->peer_lo ? engine->peer_lo_count : 0, nhi = engine->peer_hi ? engine->peer_hi_count : 0;
+        if (!engine->spatial_samples_out || nlo < 0 || nhi < 0 || nlo + nhi > engine->n_vox ||
+            (engine->peer_lo && engine->peer_lo_first != engine->w_begin) ||
+            (engine->peer_hi && engine->peer_hi_first != engine->w_begin + engine->n_vox - nhi)) {
+            set_error("peer_lo / peer_hi need spatial_samples_out and must name the first / last owned voxels of the launch");
+            return SVBASL_E_INVALID;
+        }
+    }
+    if (hyper) {
+        if (!adam || !mrf_mask(engine) || !engine->ak_grad || !engine->step_dev || hyper->step_dev != engine->step_dev ||
+            hyper->log_ak != engine->log_ak || !hyper->m || !hyper->v || !hyper->lr_t || !hyper->done_ctas ||
+            hyper->n_spatial < 1 || hyper->n_spatial > SVBASL_MAX_SPATIAL || hyper->world < 1 ||
+            hyper->world > SVBASL_MAX_PEERS || hyper->rank < 0 || hyper->rank >= hyper->world ||
+            (hyper->world > 1 && !hyper->status)) {
+            set_error("bad svbasl_hyper descriptor (needs a spatial prior, ak_grad, the engine's step_dev and log_ak)");
+            return SVBASL_E_INVALID;
+        }
+        for (int r = 0; r < hyper->world && hyper->world > 1; ++r)
+            if (!hyper->mailboxes[r]) { set_error("mailbox of rank %d is NULL", r); return SVBASL_E_INVALID; }
+        a.hy = *hyper;
     }
     a.step = step;
     a.cost = cost;
@@ -388,6 +371,12 @@ int svbasl_step(const svbasl_model *model, const svbasl_engine *engine, const sv
                 long long *nan_count, void *stream) {
     if (!adam) { set_error("null adam descriptor"); return SVBASL_E_INVALID; }
     return run_step(model, engine, adam, 0, nullptr, nullptr, cost_sum, nan_count, stream);
+}
+
+int svbasl_step_spatial(const svbasl_model *model, const svbasl_engine *engine, const svbasl_adam *adam,
+                        const svbasl_hyper *hyper, double *cost_sum, long long *nan_count, void *stream) {
+    if (!adam) { set_error("null adam descriptor"); return SVBASL_E_INVALID; }
+    return run_step(model, engine, adam, 0, nullptr, nullptr, cost_sum, nan_count, stream, hyper);
 }
 
 int svbasl_sample_spatial(const svbasl_engine *engine, int64_t n_local, int64_t step, float *out, void *stream) {
@@ -435,14 +424,16 @@ int svbasl_hyper_step_peers(float *log_ak, float *m, float *v, double *ak_grad, 
         set_error("bad hyper_step_peers arguments");
         return SVBASL_E_INVALID;
     }
-    PeerBoxes pb;
-    memset(&pb, 0, sizeof(pb));
+    svbasl_hyper hy;
+    memset(&hy, 0, sizeof(hy));
     for (int r = 0; r < world; ++r) {
         if (!mailboxes[r]) { set_error("mailbox of rank %d is NULL", r); return SVBASL_E_INVALID; }
-        pb.box[r] = (MailSlot *)mailboxes[r];
+        hy.mailboxes[r] = mailboxes[r];
     }
-    hyper_step_peers_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pb, rank, world, log_ak, m, v, ak_grad, n, grad_scale, lr_t,
-                                                              step_dev, beta1, beta2, epsilon, status);
+    hy.log_ak = log_ak; hy.m = m; hy.v = v; hy.lr_t = lr_t; hy.step_dev = step_dev;
+    hy.beta1 = beta1; hy.beta2 = beta2; hy.epsilon = epsilon;
+    hy.n_spatial = n; hy.rank = rank; hy.world = world; hy.status = status;
+    hyper_step_peers_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(hy, ak_grad, grad_scale);
     return check_launch("hyper_step_peers_kernel");
 }
 
@@ -567,7 +558,8 @@ int svbasl_host_ctx_destroy(svbasl_host_ctx *c) {
 }
 
 int svbasl_step_host(svbasl_host_ctx *c, const svbasl_model *model, const svbasl_engine *engine, const svbasl_adam *adam,
-                     const float *host_data, const float *host_tpts, const float *host_ti, double *host_cost_sum) {
+                     const svbasl_hyper *hyper, const float *host_data, const float *host_tpts, const float *host_ti,
+                     double *host_cost_sum) {
     if (!c || !engine || !adam || !host_data || (!host_tpts && !host_ti)) { set_error("null argument"); return SVBASL_E_INVALID; }
     if (engine->ld != c->ld || engine->n_batch != c->n_batch) { set_error("engine does not match the host context"); return SVBASL_E_INVALID; }
     const int s = c->slot;
@@ -585,12 +577,13 @@ int svbasl_step_host(svbasl_host_ctx *c, const svbasl_model *model, const svbasl
     if (!host_tpts) e.ti = c->d_ti[s];            // e.zoff stays the caller's resident per-voxel slice offset
     e.t_row0 = 0;
     e.t_row_stride = 1;
+    e.cost_sum_scalar = 1;
     svbasl_adam ad = *adam;
     ad.n_iters = 1;
     ad.n_batches = 1;
     double *d_cost = host_cost_sum ? c->d_cost + s : nullptr;
     if (d_cost) CUDA_TRY(cudaMemsetAsync(d_cost, 0, sizeof(double), c->run_stream));
-    int rc = svbasl_step(model, &e, &ad, d_cost, nullptr, c->run_stream);
+    int rc = svbasl_step_spatial(model, &e, &ad, hyper, d_cost, nullptr, c->run_stream);
     if (rc) return rc;
     if (d_cost) CUDA_TRY(cudaMemcpyAsync(host_cost_sum, d_cost, sizeof(double), cudaMemcpyDeviceToHost, c->run_stream));
     CUDA_TRY(cudaEventRecord(c->consumed[s], c->run_stream));

@@ -28,7 +28,68 @@ struct StepArgs {
     float *grad;             // [n_state][ld] or NULL
     double *cost_sum;        // [n_iters] or NULL
     long long *nan_count;    // [1] or NULL
+    svbasl_hyper hy;         // fused tail of a spatial iteration; hy.done_ctas == NULL: none
 };
+
+// Mailbox of one rank for the all-reduce of d(cost)/d(log ak) over NVLink peer memory: [2 parities][world] slots;
+// slot q of parity p is written by rank q only.
+struct MailSlot {
+    double val[SVBASL_MAX_SPATIAL];
+    unsigned long long seq;
+};
+
+// All-reduce of ak_grad over the ranks' mailboxes + TF-Adam step on log ak + reset of the accumulators + advance of
+// the iteration counter.  Called by ONE CTA (threads r < world each serve one rank) once every step kernel of this
+// rank's iteration has finished: as the tail of the step kernel's last CTA (svbasl_step_spatial) or as a launch of
+// its own (svbasl_hyper_step_peers).  Every rank stores its partial sums and a sequence number (= step + 1) into ITS
+// slot of every rank's mailbox (double-buffered by parity), waits - bounded - until all slots of its own mailbox carry
+// that number, and adds them in rank order in double precision: bit-identical on every rank.  The flag is stored
+// behind a system-scope fence, i.e. behind this GPU's earlier peer stores (the mirrored halo samples), so the same
+// wait is the barrier that makes the neighbours' halo data visible before the next iteration.
+__device__ __forceinline__ void hyper_tail(const svbasl_hyper &hy, double *ak_grad, float grad_scale, double (*part)[SVBASL_MAX_SPATIAL]) {
+    const int r = threadIdx.x;
+    const int n = hy.n_spatial, world = hy.world;
+    const long long step = *hy.step_dev;
+    if (world > 1) {
+        const unsigned long long seq = (unsigned long long)step + 1ull;
+        const int par = (int)(seq & 1ull);
+        if (r < world) {
+            MailSlot *dst = (MailSlot *)hy.mailboxes[r] + (size_t)par * world + hy.rank;
+            for (int k = 0; k < n; ++k) ((volatile double *)dst->val)[k] = ak_grad[k];
+            __threadfence_system();                   // values (and this GPU's earlier peer stores) before the flag
+            *(volatile unsigned long long *)&dst->seq = seq;
+            const MailSlot *src = (const MailSlot *)hy.mailboxes[hy.rank] + (size_t)par * world + r;
+            const volatile unsigned long long *flag = &src->seq;
+            if (*(volatile int *)hy.status == 0) {
+                const long long t0 = clock64();
+                while (*flag != seq) {
+                    if (clock64() - t0 > 20000000000ll) {   // ~10 s at 1.9 GHz
+                        atomicExch(hy.status, 1);
+                        break;
+                    }
+                }
+            }
+            __threadfence_system();
+            for (int k = 0; k < n; ++k) part[r][k] = ((const volatile double *)src->val)[k];
+        }
+    } else if (r == 0) {
+        for (int k = 0; k < n; ++k) part[0][k] = ak_grad[k];
+    }
+    __syncthreads();
+    if (r < n) {
+        double sum = 0.0;
+        for (int q = 0; q < world; ++q) sum += part[q][r];
+        const float g = (float)(sum * (double)grad_scale);
+        const float mm = hy.beta1 * hy.m[r] + (1.0f - hy.beta1) * g;
+        const float vv = hy.beta2 * hy.v[r] + (1.0f - hy.beta2) * g * g;
+        hy.m[r] = mm;
+        hy.v[r] = vv;
+        hy.log_ak[r] -= hy.lr_t[step] * mm / (sqrtf(vv) + hy.epsilon);
+        ak_grad[r] = 0.0;
+    }
+    __syncthreads();
+    if (r == 0) *hy.step_dev = step + 1;
+}
 
 struct EvalArgs {
     DevModel md;
@@ -111,7 +172,14 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
     const bool update = LEAN || a.update;
     const int64_t local = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool live = local < a.e.n_vox;
-    const int64_t w = a.e.w_begin + (live ? local : 0);
+    int64_t idx = live ? local : 0;
+    if (SPATIAL && (a.e.peer_lo || a.e.peer_hi)) {
+        // shard-boundary voxels (the first peer_lo_count and the last peer_hi_count owned voxels) are given to the
+        // first CTAs, so their stores into the neighbour ranks' halos cross NVLink while the interior computes
+        const int64_t nlo = a.e.peer_lo ? a.e.peer_lo_count : 0, nhi = a.e.peer_hi ? a.e.peer_hi_count : 0;
+        if (idx >= nlo) idx = idx < nlo + nhi ? a.e.n_vox - nhi + (idx - nlo) : idx - nhi;
+    }
+    const int64_t w = a.e.w_begin + idx;
     const int n_state = a.n_state;
     float *m_sm = mv_tile + threadIdx.x;
     float *v_sm = mv_tile + (size_t)n_state * kBlock + threadIdx.x;
@@ -158,7 +226,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
     const int n_iters = update ? a.ad.n_iters : 1;
     int skipped = 0;
     const int64_t step_base = a.e.step_dev ? (int64_t)*a.e.step_dev : a.step;   // device counter under graph replay
-    double *cost_sum = a.cost_sum ? a.cost_sum + (a.e.step_dev ? step_base : 0) : nullptr;
+    double *cost_sum = a.cost_sum ? a.cost_sum + ((a.e.step_dev && !a.e.cost_sum_scalar) ? step_base : 0) : nullptr;
     for (int it = 0; it < n_iters; ++it) {
         const int64_t step = step_base + it;
         const int row0 = (update && a.ad.n_batches > 1) ? (int)(step % a.ad.n_batches) : a.e.t_row0;
@@ -175,14 +243,14 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
                         vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, true, m_sm, v_sm, kBlock, a.ad.m + w, a.ad.v + w, a.e.ld);
                     else
                         vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, false, m_sm, v_sm, kBlock, m_sm, v_sm, kBlock);
-                    if (SPATIAL && it == n_iters - 1) vs.mirror_to_peers(a.e, w);
+                    if (SPATIAL && it == n_iters - 1 && a.e.spatial_samples_out) vs.store_next_samples(a.e, a.ec, w, step + 1);
                 } else {
                     ++skipped;
                     if (it == n_iters - 1) {
                         vs.store_state(a.e, w);
-                        // the neighbour rank's halo column ping-pongs like our own buffers: it needs this
-                        // iteration's (unchanged) value too, or it keeps the one from two iterations ago
-                        if (SPATIAL) vs.mirror_to_peers(a.e, w);
+                        // the next iteration's samples are still due (unchanged state, new draws): the sample
+                        // buffers - our own and the neighbour rank's halo columns - ping-pong every iteration
+                        if (SPATIAL && a.e.spatial_samples_out) vs.store_next_samples(a.e, a.ec, w, step + 1);
                         if (n_iters > 1) {                     // moments of the earlier fused iterations
                             for (int k = 0; k < n_state; ++k) {
                                 a.ad.m[(int64_t)k * a.e.ld + w] = m_sm[k * kBlock];
@@ -205,6 +273,27 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
         }
     }
     if (a.nan_count && skipped) atomicAdd((unsigned long long *)a.nan_count, (unsigned long long)skipped);
+    if constexpr (SPATIAL) {
+        if (a.hy.done_ctas) {
+            // Fused tail of the iteration: the last CTA of this launch to get here owns the hyper-parameter step.
+            // (threadFenceReduction pattern: every thread's global / peer stores are fenced, the CTA joins, thread 0
+            // publishes the CTA's completion; the CTA that observes the full count has all others' results visible.)
+            __shared__ int is_last;
+            __shared__ double part[SVBASL_MAX_PEERS][SVBASL_MAX_SPATIAL];
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned prev = atomicAdd(a.hy.done_ctas, 1u);
+                is_last = prev == gridDim.x - 1;
+                if (is_last) *a.hy.done_ctas = 0u;
+            }
+            __syncthreads();
+            if (is_last) {
+                __threadfence();
+                hyper_tail(a.hy, a.e.ak_grad, a.e.grad_scale, part);
+            }
+        }
+    }
 }
 
 // Pre-pass for spatial priors: theta samples of every spatially-regularised parameter, all local voxels

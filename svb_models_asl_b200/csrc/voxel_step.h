@@ -436,27 +436,48 @@ struct VoxelStep {
         }
     }
 
-    // Fused halo "exchange": a shard-boundary voxel also stores its updated state into the adjacent rank's halo
-    // columns through NVLink peer memory (svbasl_engine.peer_*).  
-    SVB_HD void mirror_to_peers(const svbasl_engine &e, int64_t w) const {
-        if (e.peer_lo && w >= e.peer_lo_first && w < e.peer_lo_first + e.peer_lo_count)
-            write_rows(e, e.peer_lo + (w + e.peer_lo_shift), e.peer_lo_ld);
-        if (e.peer_hi && w >= e.peer_hi_first && w < e.peer_hi_first + e.peer_hi_count)
-            write_rows(e, e.peer_hi + (w + e.peer_hi_shift), e.peer_hi_ld);
-    }
-
-    SVB_HD void write_rows(const svbasl_engine &e, float *s, int64_t ld) const {
-        int a = 0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            s[(int64_t)i * ld] = mu[i];
-            s[(int64_t)(N + i) * ld] = lv[i];
-        }
-#pragma unroll
-        for (int k = 0; k < NL; ++k) s[(int64_t)(2 * N + k) * ld] = od[k];
+    // Samples of the NEXT iteration for the spatial prior, from the state this step has just produced:
+    // theta_{p,s}(step+1) = mu_p + sum_j L_pj eps_j,s with the draws of step+1 (the same arithmetic, term by term, as
+    // the pre-pass sample_theta / spatial_sample_kernel), stored to e.spatial_samples_out [slot][S][ld] - the buffer the
+    // neighbours read in the next launch - and, for a shard-boundary voxel, ALSO into the adjacent rank's halo column
+    // through NVLink peer memory (svbasl_engine.peer_*): the halo "exchange" is these stores, no launch of its own.
+    SVB_HD void store_next_samples(const svbasl_engine &e, const EngineConst &ec, int64_t w, int64_t next_step) const {
+        int pmax = -1;
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            if (e.prior_type[i] == SVBASL_PRIOR_ARD) s[(int64_t)(2 * N + NL + a++) * ld] = lphi[i];
+            if (e.prior_type[i] == SVBASL_PRIOR_MRF) pmax = i;
+        if (pmax < 0) return;
+        const uint32_t key = rng_key(e.seed, next_step);
+        const int S = e.n_samples;
+        float sdn[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) sdn[i] = (e.prior_type[i] == SVBASL_PRIOR_MRF) ? fexp(0.5f * lv[i]) : 0.0f;
+        float *own = e.spatial_samples_out + w;
+        float *lo = (e.peer_lo && w >= e.peer_lo_first && w < e.peer_lo_first + e.peer_lo_count)
+                        ? e.peer_lo + (w + e.peer_lo_shift) : nullptr;
+        float *hi = (e.peer_hi && w >= e.peer_hi_first && w < e.peer_hi_first + e.peer_hi_count)
+                        ? e.peer_hi + (w + e.peer_hi_shift) : nullptr;
+        for (int s = 0; s < S; ++s) {
+            float eps[N + 1];
+#pragma unroll
+            for (int k = 0; k < (N + 1) / 2; ++k)
+                if (2 * k <= pmax) normal2(key, e.vox_offset + w, s, k, eps[2 * k], eps[2 * k + 1]);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                if (e.prior_type[i] != SVBASL_PRIOR_MRF) continue;
+                float th = mu[i];
+#pragma unroll
+                for (int j = 0; j < i; ++j) th += od[stri(i, j)] * eps[j];
+                th += sdn[i] * eps[i];
+                const int64_t row = (int64_t)ec.sp_slot[i] * S + s;
+                own[row * e.ld] = th;
+                if (lo) lo[row * e.peer_lo_ld] = th;
+                if (hi) hi[row * e.peer_hi_ld] = th;
+            }
+        }
+#if defined(__CUDA_ARCH__)
+        if (lo || hi) __threadfence_system();        // peer stores ordered before this CTA reports completion
+#endif
     }
 
     SVB_HD void store_state(const svbasl_engine &e, int64_t w) const {

@@ -165,6 +165,13 @@ class FusedSvb:
 
     All arrays are SoA, voxel-fastest, row stride `ld`.  `state` rows: mean[P'], logvar[P'], off-diagonal
     Cholesky rows, ARD log-phi rows (include/svbasl.h).
+
+    Spatial ("M") priors: the same single launch additionally (a) reads the six neighbours' theta samples of this
+    iteration from `sp_bufs[sp_cur]`, (b) writes every voxel's samples of the NEXT iteration into the other buffer -
+    and, sharded over several GPUs, straight into the adjacent ranks' halo columns over NVLink peer memory - and (c)
+    ends with the all-reduce of d(cost)/d(log ak) over peer-memory mailboxes, the Adam step on log ak and the advance
+    of the device-resident iteration counter (svbasl_step_spatial).  `halo_mode`: "peer" (that), "peer+nccl" (peer
+    stores, NCCL all-reduce + separate hyper-step launch), "nccl" (NCCL send/recv of the halo samples, NCCL all-reduce).
     """
 
     def __init__(self, model, data, tpts=None, *, ti=None, zoff=None, n_samples=10, batch_size=None,
@@ -211,8 +218,6 @@ class FusedSvb:
         self.step_count = 0
         z = lambda *s, dt=torch.float32: torch.zeros(*s, device=self.dev, dtype=dt)  # noqa: E731
         self.state = z(self.n_state, self.ld)
-        self.state_alt = z(self.n_state, self.ld) if self.mrf else None
-        self._buf_alt0 = self.state_alt
         self.m = z(self.n_state, self.ld)
         self.v = z(self.n_state, self.ld)
         steps = np.arange(1, max_steps + 1, dtype=np.float64)
@@ -222,27 +227,33 @@ class FusedSvb:
         self.cost_hist = z(max_steps + self.max_fuse, dt=torch.float64)   # summed cost of every iteration
         self.nan_count = z(1, dt=torch.int64)
         self.neighbours = device_array(neighbours, self.dev, torch.int32) if neighbours is not None else None
+        self.eps = None
+        self.plan = None            # ShardPlan of a spatial prior sharded over several ranks
+        self.halo_mode = None
+        self.reduce_fn = None       # sums a small tensor over all ranks in place (NCCL / gloo)
+        self.graphs = None          # enable_graph(): one CUDA-graph replay per spatial iteration
+        self.peers = None
+        self._shared = []
         if self.mrf:
             if self.neighbours is None:
                 raise ValueError("spatial prior needs a neighbour table")
-            self.log_ak = torch.full((len(self.mrf),), math.log(ak_init), device=self.dev, dtype=torch.float32)
-            self.ak_m, self.ak_v = z(len(self.mrf)), z(len(self.mrf))
+            n_sp = len(self.mrf)
+            self.log_ak = torch.full((n_sp,), math.log(ak_init), device=self.dev, dtype=torch.float32)
+            self.ak_m, self.ak_v = z(n_sp), z(n_sp)
             self.ak_grad = z(L.MAX_SPATIAL, dt=torch.float64)
-            self.sp_samples = z(len(self.mrf), self.S, self.ld)
+            # neighbour-sample buffers [n_sp, S, ld], ping-pong: iteration t reads sp_bufs[sp_cur] and writes the
+            # samples of t+1 into the other one
+            self.sp_bufs = [z(n_sp, self.S, self.ld), z(n_sp, self.S, self.ld)]
+            self.sp_cur, self.sp_valid = 0, False
+            self.step_dev = z(1, dt=torch.int64)                          # iteration counter, device resident
+            self.done_ctas = z(1, dt=torch.int32)
+            self.peer_status = z(1, dt=torch.int32)
         else:
-            self.log_ak = self.ak_grad = self.sp_samples = None
-        self.eps = None
-        # multi-GPU hooks (svb_models_asl_b200/sharding.py): halo_exchange(state) refreshes the halo columns from
-        # the adjacent ranks; reduce_fn(tensor) sums a small tensor over all ranks in place
-        self.halo_exchange = None
-        self.reduce_fn = None
-        self.plan = None            # set by enable_overlap(): boundary-first launches + comm stream
-        self.graphs = None          # set by enable_graph(): one CUDA-graph replay per spatial iteration
-        self._capturing = False
-        self.peers = None
+            self.log_ak = self.ak_grad = self.sp_bufs = None
 
     # ---- descriptors ----
-    def engine_desc(self, row0=0):
+    def engine_desc(self, row0=0, for_step=False):
+        """`for_step`: descriptor of a fused spatial iteration (device counter, next-sample buffer, peer pointers)."""
         e = L.Engine()
         e.n_vox, e.w_begin, e.ld = self.n_vox, self.halo[0], self.ld
         e.vox_offset = self.vox_offset - self.halo[0]
@@ -256,7 +267,6 @@ class FusedSvb:
         e.ard_phi_max, e.latent_weight = self.ard_phi_max, self.latent_weight
         e.grad_scale = 1.0 / self.n_vox_global
         e.state = self.state.data_ptr()
-        e.state_out = self.state_alt.data_ptr() if self.mrf else None
         e.data = self.data.data_ptr()
         e.tpts = self.tpts.data_ptr() if self.tpts is not None else None
         e.ti = self.ti.data_ptr() if self.ti is not None else None
@@ -264,12 +274,25 @@ class FusedSvb:
         e.t_row0, e.t_row_stride = row0, self.n_batches
         e.eps = self.eps.data_ptr() if self.eps is not None else None
         e.seed = self.seed
-        e.neighbours = self.neighbours.data_ptr() if self.neighbours is not None else None
-        e.spatial_samples = self.sp_samples.data_ptr() if self.sp_samples is not None else None
-        e.log_ak = self.log_ak.data_ptr() if self.log_ak is not None else None
-        e.ak_grad = self.ak_grad.data_ptr() if self.ak_grad is not None else None
-        if self.graphs is not None or self._capturing:
-            e.step_dev = self.step_dev.data_ptr()
+        if self.mrf:
+            e.neighbours = self.neighbours.data_ptr()
+            e.spatial_samples = self.sp_bufs[self.sp_cur].data_ptr()
+            e.log_ak = self.log_ak.data_ptr()
+            e.ak_grad = self.ak_grad.data_ptr()
+            if for_step:
+                e.step_dev = self.step_dev.data_ptr()
+                e.spatial_samples_out = self.sp_bufs[1 - self.sp_cur].data_ptr()
+                if self.peers:
+                    for side in ("lo", "hi"):
+                        if side in self.peers:
+                            p = self.peers[side]
+                            # the neighbour's buffer that plays the "next samples" role in the same iteration
+                            setattr(e, "peer_" + side, p["ptrs"][1 - self.sp_cur])
+                            setattr(e, "peer_%s_ld" % side, p["ld"])
+                            setattr(e, "peer_%s_shift" % side, p["shift"])
+                            first, count = self._mirror[side]
+                            setattr(e, "peer_%s_first" % side, first)
+                            setattr(e, "peer_%s_count" % side, count)
         return e
 
     def adam_desc(self, n_iters=1):
@@ -278,6 +301,22 @@ class FusedSvb:
         ad.beta1, ad.beta2, ad.epsilon = self.b1, self.b2, self.adam_eps
         ad.step0, ad.n_iters, ad.n_batches = self.step_count, n_iters, self.n_batches
         return ad
+
+    def hyper_desc(self):
+        """Fused tail of a spatial iteration (svbasl_hyper): single GPU (world = 1) or over the ranks' mailboxes."""
+        h = L.Hyper()
+        h.log_ak, h.m, h.v = self.log_ak.data_ptr(), self.ak_m.data_ptr(), self.ak_v.data_ptr()
+        h.lr_t, h.step_dev, h.done_ctas = self.lr_t.data_ptr(), self.step_dev.data_ptr(), self.done_ctas.data_ptr()
+        h.beta1, h.beta2, h.epsilon = self.b1, self.b2, self.adam_eps
+        h.n_spatial = len(self.mrf)
+        h.status = self.peer_status.data_ptr()
+        if self.plan is not None and self.plan.world > 1:
+            h.rank, h.world = self.plan.rank, self.plan.world
+            for r in range(self.plan.world):
+                h.mailboxes[r] = self._mail_ptrs[r]
+        else:
+            h.rank, h.world = 0, 1
+        return h
 
     # ---- state ----
     def set_posterior(self, means, variances):
@@ -295,6 +334,11 @@ class FusedSvb:
         self.v.zero_()
         self.cost_hist.zero_()
         self.step_count = 0
+        if self.mrf:
+            if self.graphs is not None:
+                raise ValueError("set_posterior() after enable_graph(): the captured launches are bound to a buffer parity")
+            self.step_dev.zero_()
+            self.sp_cur, self.sp_valid = 0, False
 
     # ---- the hot path ----
     def step(self, n_iters=1, want_cost=True):
@@ -302,249 +346,164 @@ class FusedSvb:
         per-iteration summed costs (no host sync)."""
         if self.step_count + n_iters > self.lr_t.numel():
             raise ValueError("max_steps exceeded")
-        if self.mrf and n_iters != 1:
-            raise ValueError("spatial priors couple neighbouring voxels: one iteration per launch")
+        if self.mrf:
+            if n_iters != 1:
+                raise ValueError("spatial priors couple neighbouring voxels: one iteration per launch")
+            return self._step_spatial()
         if n_iters > self.max_fuse:
             raise ValueError("at most %i fused iterations per launch" % self.max_fuse)
-        if self.graphs is not None:
-            step = self.step_count
-            self.graphs[step & 1].replay()
-            self.state, self.state_alt = self.state_alt, self.state
-            self.step_count += 1
-            return self.cost_hist[step:step + 1]
-        if self.mrf and self.plan is not None:
-            return self._step_spatial_sharded(want_cost)
         e = self.engine_desc(row0=self.step_count % self.n_batches)
         ad = self.adam_desc(n_iters)
-        if self.mrf:
-            self.ak_grad.zero_()
-            self.sample_spatial(e, self.step_count)
         cost_ptr = self.cost_hist.data_ptr() + 8 * self.step_count if want_cost else None
         L.check(self.lib.svbasl_step(C.byref(self.mdesc), C.byref(e), C.byref(ad), cost_ptr,
                                      self.nan_count.data_ptr(), _stream_ptr()))
-        if self.mrf:
-            self.state, self.state_alt = self.state_alt, self.state
-            self._hyper_step(self.reduce_fn)
-            if self.halo_exchange is not None:
-                self.halo_exchange(self.state)
         self.step_count += n_iters
         return self.cost_hist[self.step_count - n_iters:self.step_count]
 
-    # ---- spatial prior over several GPUs: boundary voxels first, halo exchange overlapped with the interior ----
-    def enable_overlap(self, plan):
-        """Shard-boundary voxels are processed first so that their new state travels to the neighbouring ranks (NCCL
-        send/recv on a side stream) while the interior is still being computed; the all-reduce of the log-ak
-        gradient and the hyper-parameter step run on the same side stream behind the interior launch."""
-        self.plan = plan
-        self.comm_stream = torch.cuda.Stream(device=self.dev)
-        self.ev_halo = self.ev_ak = None
-        self.ak_grads = [torch.zeros(L.MAX_SPATIAL, device=self.dev, dtype=torch.float64) for _ in range(2)]
-        lo_n, hi_n = plan.prev_halo_hi, plan.next_halo_lo      # owned voxels the neighbours need
-        a = self.halo[0]
-        if lo_n + hi_n >= self.n_vox:
-            self.ranges = [(a, self.n_vox)]
-            self.n_boundary = 1
-        else:
-            self.ranges = [r for r in ((a, lo_n), (a + self.n_vox - hi_n, hi_n)) if r[1] > 0]
-            self.n_boundary = len(self.ranges)
-            self.ranges.append((a + lo_n, self.n_vox - lo_n - hi_n))
-
-    def _step_spatial_sharded(self, want_cost=True):
-        main = torch.cuda.current_stream()
-        comm = self.comm_stream
-        step = self.step_count
-        self.ak_grad = self.ak_grads[step & 1]               # double-buffered: the previous one may still be in flight
-        e = self.engine_desc(row0=step % self.n_batches)
-        ad = self.adam_desc(1)
-        if self.ev_halo is not None:
-            main.wait_event(self.ev_halo)                     # halo state of the current `state` has arrived
+    # ---- spatial prior: one launch per iteration ----
+    def _prime_samples(self):
+        """First iteration after the state was set from outside: the pre-pass kernel draws this iteration's samples
+        of every local voxel, halo included (afterwards each step writes the next iteration's samples itself)."""
+        if self.plan is not None and self.plan.world > 1:
+            self.plan.exchange_halo(self.state)                # halo voxels' state from the adjacent ranks (set-up only)
+        e = self.engine_desc()
+        self.sample_spatial(e, self.step_count, self.sp_bufs[self.sp_cur])
         self.ak_grad.zero_()
-        self.sample_spatial(e, step)                          # owned + halo voxels; does not need log ak
-        if self.ev_ak is not None:
-            main.wait_event(self.ev_ak)                       # log ak of this iteration (previous hyper step)
-        cost_ptr = self.cost_hist.data_ptr() + 8 * step if want_cost else None
-        ev_bnd = torch.cuda.Event()
-        for k, (w0, n) in enumerate(self.ranges):
-            e.w_begin, e.n_vox = w0, n
-            L.check(self.lib.svbasl_step(C.byref(self.mdesc), C.byref(e), C.byref(ad), cost_ptr,
-                                         self.nan_count.data_ptr(), _stream_ptr()))
-            if k == self.n_boundary - 1:
-                ev_bnd.record(main)
-        ev_int = torch.cuda.Event()
-        ev_int.record(main)
-        self.state, self.state_alt = self.state_alt, self.state
-        with torch.cuda.stream(comm):
-            comm.wait_event(ev_bnd)
-            self.plan.exchange_halo(self.state)               # new state of the boundary voxels -> neighbours' halos
-            self.ev_halo = torch.cuda.Event()
-            self.ev_halo.record(comm)
-            comm.wait_event(ev_int)
-            self._hyper_step(self.reduce_fn)                  # all-reduce of d cost / d log ak, then its Adam step
-            self.ev_ak = torch.cuda.Event()
-            self.ev_ak.record(comm)
+        self.sp_valid = True
+        if self.plan is not None and self.plan.world > 1:
+            import torch.distributed as td
+            torch.cuda.synchronize()
+            td.barrier()                   # peer stores of the first iteration must not overtake a neighbour's pre-pass
+
+    def _launch_spatial_iteration(self):
+        """The launch(es) of one spatial iteration for the current buffer parity (also what enable_graph captures)."""
+        e = self.engine_desc(for_step=True)
+        ad = self.adam_desc(1)
+        mode = self.halo_mode if (self.plan is not None and self.plan.world > 1) else None
+        fused_tail = mode in (None, "peer")
+        hy = self.hyper_desc() if fused_tail else None
+        L.check(self.lib.svbasl_step_spatial(C.byref(self.mdesc), C.byref(e), C.byref(ad),
+                                             C.byref(hy) if hy is not None else None, self.cost_hist.data_ptr(),
+                                             self.nan_count.data_ptr(), _stream_ptr()))
+        if fused_tail:
+            return
+        if mode == "nccl":
+            nxt = self.sp_bufs[1 - self.sp_cur]
+            self.plan.exchange_halo(nxt.view(-1, self.ld))     # ncclSend/Recv of the boundary voxels' next samples
+        self.reduce_fn(self.ak_grad)                           # NCCL all-reduce (also orders the peer stores)
+        L.check(self.lib.svbasl_hyper_step_dev(self.log_ak.data_ptr(), self.ak_m.data_ptr(), self.ak_v.data_ptr(),
+                                               self.ak_grad.data_ptr(), len(self.mrf), 1.0 / self.n_vox_global,
+                                               self.lr_t.data_ptr(), self.step_dev.data_ptr(), self.b1, self.b2,
+                                               self.adam_eps, _stream_ptr()))
+
+    def _step_spatial(self):
+        if not self.sp_valid:
+            self._prime_samples()
+        step = self.step_count
+        if self.graphs is not None:
+            self.graphs[self.sp_cur].replay()
+        else:
+            self._launch_spatial_iteration()
+        self.sp_cur ^= 1
         self.step_count += 1
         return self.cost_hist[step:step + 1]
 
-    # ---- spatial prior, CUDA-graph replay, halo "exchange" fused into the step kernel over NVLink peer memory ----
-    def share_state_with_neighbours(self, plan, ak_reduce="peer"):
-        """Move both state buffers into IPC-exportable device memory and exchange the handles with the adjacent
-        ranks (once, at set-up), so that the step kernel can store boundary voxels' new state directly into the
-        neighbours' halo columns over NVLink.  ak_reduce "peer": every rank also exports a small mailbox that all
-        ranks open, and the per-iteration all-reduce of the log-ak gradient (+ barrier) runs over it inside the
-        hyper-step kernel (svbasl_hyper_step_peers); "nccl": that reduction stays an NCCL all-reduce."""
+    def shard(self, plan, halo_mode="peer", reduce_fn=None):
+        """Spatial prior sharded over the ranks of one box.  "peer" / "peer+nccl": both neighbour-sample buffers move
+        into IPC-exportable device memory and the handles are exchanged with the adjacent ranks (once), so that the
+        step kernel stores boundary voxels' samples directly into the neighbours' halo columns over NVLink; "peer"
+        also exports a small mailbox per rank for the fused all-reduce of the log-ak gradient."""
         import torch.distributed as td
-        self.ak_reduce = ak_reduce
-        n_bytes = 4 * self.n_state * self.ld
-        self._shared = []
+        if halo_mode not in ("peer", "peer+nccl", "nccl"):
+            raise ValueError("halo_mode must be 'peer', 'peer+nccl' or 'nccl'")
+        self.plan, self.halo_mode, self.reduce_fn = plan, halo_mode, reduce_fn
+        if plan.world == 1 or halo_mode == "nccl":
+            return
+        if plan.world > L.MAX_PEERS:
+            raise ValueError("peer-memory modes support at most %d ranks" % L.MAX_PEERS)
+        n_bytes = 4 * self.sp_bufs[0].numel()
         handles = []
-        for name in ("state", "state_alt"):
+        for k in (0, 1):
             ptr = C.c_void_p()
             handle = (C.c_ubyte * 64)()
             with torch.cuda.device(self.dev):
                 L.check(self.lib.svbasl_shared_alloc(n_bytes, C.byref(ptr), handle))
-            view = _DevicePointer(ptr.value, (self.n_state, self.ld))
+            view = _DevicePointer(ptr.value, tuple(self.sp_bufs[k].shape))
             t = torch.as_tensor(view, device=self.dev)
-            t.copy_(getattr(self, name))
-            setattr(self, name, t)
+            t.copy_(self.sp_bufs[k])
+            self.sp_bufs[k] = t
             self._shared.append((ptr, view))
             handles.append(bytes(handle))
-        self._buf_alt0 = self.state_alt
         mine = {"rank": plan.rank, "ld": self.ld, "offset": plan.global_offset, "handles": handles}
-        if ak_reduce == "peer":
-            if plan.world > L.MAX_PEERS:
-                raise ValueError("peer-memory reduction supports at most %d ranks" % L.MAX_PEERS)
+        if halo_mode == "peer":
             ptr = C.c_void_p()
             handle = (C.c_ubyte * 64)()
             with torch.cuda.device(self.dev):
                 L.check(self.lib.svbasl_shared_alloc(self.lib.svbasl_mailbox_bytes(plan.world), C.byref(ptr), handle))
             self._mailbox = ptr
             mine["mailbox"] = bytes(handle)
-            self.peer_status = torch.zeros(1, device=self.dev, dtype=torch.int32)
         everyone = [None] * plan.world
         td.all_gather_object(everyone, mine)
-        if ak_reduce == "peer":
-            self._mail_ptrs = (C.c_void_p * plan.world)()
-            self._mail_opened = []
-            for r, info in enumerate(everyone):
-                if r == plan.rank:
-                    self._mail_ptrs[r] = self._mailbox.value
-                    continue
-                p = C.c_void_p()
-                buf = (C.c_ubyte * 64).from_buffer_copy(info["mailbox"])
-                with torch.cuda.device(self.dev):
-                    L.check(self.lib.svbasl_shared_open(buf, C.byref(p)))
-                self._mail_ptrs[r] = p.value
-                self._mail_opened.append(p.value)
+        self._opened = []
+
+        def open_handle(raw):
+            p = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(raw)
+            with torch.cuda.device(self.dev):                              # the ACCESSING device must be current
+                L.check(self.lib.svbasl_shared_open(buf, C.byref(p)))
+            self._opened.append(p.value)
+            return p.value
+
+        if halo_mode == "peer":
+            self._mail_ptrs = [self._mailbox.value if r == plan.rank else open_handle(info["mailbox"])
+                               for r, info in enumerate(everyone)]
         self.peers = {}
         for side, r in (("lo", plan.rank - 1), ("hi", plan.rank + 1)):
             if 0 <= r < plan.world:
                 info = everyone[r]
-                ptrs = []
-                for h in info["handles"]:
-                    p = C.c_void_p()
-                    buf = (C.c_ubyte * 64).from_buffer_copy(h)
-                    with torch.cuda.device(self.dev):                      # the ACCESSING device must be current
-                        L.check(self.lib.svbasl_shared_open(buf, C.byref(p)))
-                    ptrs.append(p.value)
-                self.peers[side] = {"ptrs": ptrs, "ld": info["ld"], "shift": plan.global_offset - info["offset"]}
-        self.plan = plan
+                self.peers[side] = {"ptrs": [open_handle(h) for h in info["handles"]], "ld": info["ld"],
+                                    "shift": plan.global_offset - info["offset"]}
         a = self.halo[0]
-        lo_n, hi_n = plan.prev_halo_hi, plan.next_halo_lo
+        lo_n, hi_n = plan.prev_halo_hi, plan.next_halo_lo      # owned voxels that lie in the neighbours' halos
         self._mirror = {"lo": (a, lo_n), "hi": (a + self.n_vox - hi_n, hi_n)}
-        if lo_n + hi_n >= self.n_vox:
-            self.ranges, self.n_boundary = [(a, self.n_vox)], 1
-        else:
-            self.ranges = [r for r in ((a, lo_n), (a + self.n_vox - hi_n, hi_n)) if r[1] > 0]
-            self.n_boundary = len(self.ranges)
-            self.ranges.append((a + lo_n, self.n_vox - lo_n - hi_n))
         torch.cuda.synchronize()
         td.barrier()
 
     def enable_graph(self):
-        """Capture one spatial iteration (pre-pass, step launches, all-reduce of the log-ak gradient, hyper step +
-        counter advance) as a CUDA graph per state-buffer parity; step() then costs one replay."""
+        """Capture the launch(es) of one spatial iteration as a CUDA graph per buffer parity; step() then costs one
+        replay.  The iteration index lives in device memory (step_dev), so a replay needs no new arguments."""
         if not self.mrf:
             raise ValueError("graph replay is wired for the spatial-prior iteration (the others are one launch)")
-        if self.plan is not None and self.peers is None:
-            raise ValueError("share_state_with_neighbours() first")
-        self.step_dev = torch.tensor([self.step_count], device=self.dev, dtype=torch.int64)
-        self.ak_grad.zero_()
-        if self.reduce_fn is not None:
+        if not self.sp_valid:
+            self._prime_samples()
+        if self.reduce_fn is not None and self.halo_mode in ("peer+nccl", "nccl"):
+            self.ak_grad.zero_()
             self.reduce_fn(self.ak_grad)                                  # NCCL communicator warm-up outside capture
         torch.cuda.synchronize()
-        graphs = []
-        self._fork_stream = torch.cuda.Stream(device=self.dev)
+        graphs = [None, None]
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream())
+        cur0 = self.sp_cur
         with torch.cuda.stream(side):
-            for _parity in (0, 1):
+            for _k in (0, 1):
                 g = torch.cuda.CUDAGraph()
-                self._capturing = True
                 with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
-                    self._record_iteration()
-                self._capturing = False
-                self.state, self.state_alt = self.state_alt, self.state   # the other parity's buffer roles
-                graphs.append(g)
+                    self._launch_spatial_iteration()
+                graphs[self.sp_cur] = g
+                self.sp_cur ^= 1
+        self.sp_cur = cur0
         torch.cuda.current_stream().wait_stream(side)
         self.graphs = graphs
-        if self.peers is not None:
+        if self.plan is not None and self.plan.world > 1:
             import torch.distributed as td
             torch.cuda.synchronize()
             td.barrier()                  # the peer-memory reduction waits with a time-out: start the ranks together
 
-    def _record_iteration(self):
-        e = self.engine_desc(row0=0)
-        ad = self.adam_desc(1)
-        parity_out = self.state_alt
-        if self.peers:
-            for side_name in ("lo", "hi"):
-                if side_name in self.peers:
-                    p = self.peers[side_name]
-                    # the neighbour's buffer that plays the state_out role in the same iteration
-                    idx = 1 if parity_out is self._buf_alt0 else 0
-                    setattr(e, "peer_" + side_name, p["ptrs"][idx])
-                    setattr(e, "peer_%s_ld" % side_name, p["ld"])
-                    setattr(e, "peer_%s_shift" % side_name, p["shift"])
-                    first, count = self._mirror[side_name]
-                    setattr(e, "peer_%s_first" % side_name, first)
-                    setattr(e, "peer_%s_count" % side_name, count)
-        self.sample_spatial(e, 0)
-        ranges = self.ranges if self.plan is not None else [(self.halo[0], self.n_vox)]
-
-        def launch(w0, n):
-            e.w_begin, e.n_vox = w0, n
-            L.check(self.lib.svbasl_step(C.byref(self.mdesc), C.byref(e), C.byref(ad), self.cost_hist.data_ptr(),
-                                         self.nan_count.data_ptr(), _stream_ptr()))
-
-        if len(ranges) > 1:
-            # the thin boundary launches run on a forked branch of the graph, concurrently with the interior
-            cur = torch.cuda.current_stream()
-            fork = self._fork_stream
-            ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
-            ev_fork.record(cur)
-            fork.wait_event(ev_fork)
-            with torch.cuda.stream(fork):
-                for (w0, n) in ranges[:-1]:
-                    launch(w0, n)
-                ev_join.record(fork)
-            launch(*ranges[-1])
-            cur.wait_event(ev_join)
-        else:
-            launch(*ranges[0])
-        if self.peers is not None and getattr(self, "ak_reduce", "nccl") == "peer":
-            # all-reduce of the log-ak gradient over the ranks' mailboxes (NVLink peer memory) + its Adam step
-            L.check(self.lib.svbasl_hyper_step_peers(
-                self.log_ak.data_ptr(), self.ak_m.data_ptr(), self.ak_v.data_ptr(), self.ak_grad.data_ptr(),
-                len(self.mrf), 1.0 / self.n_vox_global, self.lr_t.data_ptr(), self.step_dev.data_ptr(), self.b1, self.b2,
-                self.adam_eps, self.plan.rank, self.plan.world, self._mail_ptrs, self.peer_status.data_ptr(),
-                _stream_ptr()))
-            return
-        if self.reduce_fn is not None:
-            self.reduce_fn(self.ak_grad)
-        L.check(self.lib.svbasl_hyper_step_dev(self.log_ak.data_ptr(), self.ak_m.data_ptr(), self.ak_v.data_ptr(),
-                                               self.ak_grad.data_ptr(), len(self.mrf), 1.0 / self.n_vox_global,
-                                               self.lr_t.data_ptr(), self.step_dev.data_ptr(), self.b1, self.b2,
-                                               self.adam_eps, _stream_ptr()))
+    def check_peers(self):
+        """Raise if a rank failed to arrive at the peer-memory all-reduce within its time-out (host sync)."""
+        if self.mrf and int(self.peer_status.item()) != 0:
+            raise L.SvbAslError("spatial iteration: a rank did not arrive at the all-reduce of the log-ak gradient "
+                                "within the time-out; the results of this run are invalid")
 
     def release(self):
         """Tear down graph / peer-memory resources (before the process group is destroyed): captured graphs hold
@@ -552,68 +511,56 @@ class FusedSvb:
         import torch.distributed as td
         torch.cuda.synchronize()
         self.graphs = None
+        timed_out = bool(self.mrf) and int(self.peer_status.item()) != 0
         if self.peers is not None:
-            timed_out = getattr(self, "peer_status", None) is not None and int(self.peer_status.item()) != 0
-            for p in self.peers.values():
-                for ptr in p["ptrs"]:
-                    self.lib.svbasl_shared_close(C.c_void_p(ptr))
-            for ptr in getattr(self, "_mail_opened", []):
+            for ptr in getattr(self, "_opened", []):
                 self.lib.svbasl_shared_close(C.c_void_p(ptr))
-            self._mail_opened = []
+            self._opened = []
             self.peers = None
             if td.is_available() and td.is_initialized():
                 td.barrier()                       # every neighbour has closed its mapping of our buffers
-            keep = getattr(self, "_shared", [])
-            self.state, self.state_alt = self.state.clone(), self.state_alt.clone()
-            self._buf_alt0 = self.state_alt
-            for ptr, _view in keep:
+            self.sp_bufs = [b.clone() for b in self.sp_bufs]
+            for ptr, _view in self._shared:
                 self.lib.svbasl_shared_free(ptr)
             self._shared = []
             if getattr(self, "_mailbox", None) is not None:
                 self.lib.svbasl_shared_free(self._mailbox)
                 self._mailbox = None
-            if timed_out:
-                raise L.SvbAslError("svbasl_hyper_step_peers: a rank did not arrive within the time-out; the "
-                                    "spatial-prior results of this run are invalid")
+            self.halo_mode = "nccl"                # still usable, through NCCL
         torch.cuda.synchronize()
+        if timed_out:
+            raise L.SvbAslError("spatial iteration: a rank did not arrive at the all-reduce of the log-ak gradient "
+                                "within the time-out; the results of this run are invalid")
 
     def finish(self):
-        """Join the side stream (call before reading state / log_ak after sharded spatial steps)."""
-        if self.plan is not None and getattr(self, "comm_stream", None) is not None:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        """Kept for callers of the round-1 API: every launch of an iteration is on the current stream."""
 
-    def _hyper_step(self, reduce_fn=None):
-        if reduce_fn is not None:
-            reduce_fn(self.ak_grad)
-        lr_t = float(self.lr_t_host[self.step_count])
-        L.check(self.lib.svbasl_hyper_step(self.log_ak.data_ptr(), self.ak_m.data_ptr(), self.ak_v.data_ptr(),
-                                           self.ak_grad.data_ptr(), len(self.mrf), 1.0 / self.n_vox_global, lr_t,
-                                           self.b1, self.b2, self.adam_eps, _stream_ptr()))
-
-    def sample_spatial(self, e, step):
+    def sample_spatial(self, e, step, out):
         """Pre-pass: theta samples of the spatially regularised parameters for all local voxels (halo included)."""
-        L.check(self.lib.svbasl_sample_spatial(C.byref(e), self.ld, step, self.sp_samples.data_ptr(), _stream_ptr()))
+        L.check(self.lib.svbasl_sample_spatial(C.byref(e), self.ld, step, out.data_ptr(), _stream_ptr()))
 
     def elbo_grad(self, step=None, row0=0):
         """-> (cost [ld], grad [n_state, ld]) without updating anything."""
-        self.finish()
         e = self.engine_desc(row0=row0)
-        e.state_out = None
         cost = torch.zeros(self.ld, device=self.dev)
         grad = torch.zeros(self.n_state, self.ld, device=self.dev)
+        step = self.step_count if step is None else step
         if self.mrf:
-            # the log-ak gradient of this evaluation goes to a scratch accumulator: the running one must stay zero
-            # between iterations (the graph-replayed iteration zeroes it at its END, svbasl_hyper_step_dev)
+            # this evaluation's neighbour samples and log-ak gradient go to scratch buffers: the running ones belong
+            # to the iteration in flight
+            if self.plan is not None and self.plan.world > 1:
+                self.plan.exchange_halo(self.state)
+            scratch = torch.empty_like(self.sp_bufs[0])
             self.ak_grad_eval = torch.zeros_like(self.ak_grad)
             e.ak_grad = self.ak_grad_eval.data_ptr()
-            self.sample_spatial(e, self.step_count if step is None else step)
-        L.check(self.lib.svbasl_elbo_grad(C.byref(self.mdesc), C.byref(e), self.step_count if step is None else step,
-                                          cost.data_ptr(), grad.data_ptr(), None, _stream_ptr()))
+            e.spatial_samples = scratch.data_ptr()
+            self.sample_spatial(e, step, scratch)
+        L.check(self.lib.svbasl_elbo_grad(C.byref(self.mdesc), C.byref(e), step, cost.data_ptr(), grad.data_ptr(), None,
+                                          _stream_ptr()))
         return cost, grad
 
     def model_fit(self):
         """Prediction at the posterior mean for every time point -> [T, ld]"""
-        self.finish()
         e = self.engine_desc()
         out = torch.zeros(self.T, self.ld, device=self.dev)
         L.check(self.lib.svbasl_model_fit(C.byref(self.mdesc), C.byref(e), out.data_ptr(), _stream_ptr()))
@@ -636,7 +583,6 @@ class FusedSvb:
     # ---- results ----
     def posterior_mean(self):
         """Model-space posterior means [P, n_vox] (transform applied) and internal means/variances."""
-        self.finish()
         sl = slice(self.halo[0], self.halo[0] + self.n_vox)
         return self.state[:self.N, sl], torch.exp(self.state[self.N:2 * self.N, sl])
 
@@ -647,11 +593,14 @@ class HostFeeder:
     batch's data rows (pinned host memory) to the device on a copy stream while the previous iteration computes,
     runs the fused step and copies the summed cost back (svbasl_step_host).  Time points travel either as a full
     [B, ld] array or in the model's low-rank form (the batch's TIs; the per-voxel slice offset stays resident).
+    Spatial priors run through the same call (single GPU or peer-memory sharding: the iteration is one launch).
     """
 
     def __init__(self, fused):
         self.f = fused
         self.lib = fused.lib
+        if fused.mrf and fused.plan is not None and fused.plan.world > 1 and fused.halo_mode != "peer":
+            raise ValueError("host-fed spatial iterations over several ranks need halo_mode 'peer' (one launch)")
         self.ctx = C.c_void_p()
         L.check(self.lib.svbasl_host_ctx_create(C.byref(self.ctx), fused.ld, fused.B))
         self.cost = torch.zeros(2, dtype=torch.float64).pin_memory()
@@ -660,17 +609,24 @@ class HostFeeder:
     def step(self, host_data, host_tpts=None, host_ti=None, zoff_dev=None):
         """host_data [B, ld] (pinned); host_tpts [B, ld] (pinned) or host_ti [B] (pinned) + zoff_dev [ld] or None."""
         f = self.f
+        hy = None
         if f.mrf:
-            raise ValueError("host-fed steps do not support spatial priors (pre-pass / hyper step run per iteration)")
-        e = f.engine_desc()
+            if not f.sp_valid:
+                f._prime_samples()
+            torch.cuda.current_stream().synchronize() if self.calls == 0 else None
+            hy = f.hyper_desc()
+        e = f.engine_desc(for_step=bool(f.mrf))
         if host_tpts is None:
             e.tpts = None
             e.zoff = zoff_dev.data_ptr() if zoff_dev is not None else None
         ad = f.adam_desc(1)
-        L.check(self.lib.svbasl_step_host(self.ctx, C.byref(f.mdesc), C.byref(e), C.byref(ad), host_data.data_ptr(),
+        L.check(self.lib.svbasl_step_host(self.ctx, C.byref(f.mdesc), C.byref(e), C.byref(ad),
+                                          C.byref(hy) if hy is not None else None, host_data.data_ptr(),
                                           host_tpts.data_ptr() if host_tpts is not None else None,
                                           host_ti.data_ptr() if host_ti is not None else None,
                                           self.cost.data_ptr() + 8 * (self.calls & 1)))
+        if f.mrf:
+            f.sp_cur ^= 1
         f.step_count += 1
         self.calls += 1
 

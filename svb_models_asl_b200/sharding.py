@@ -33,7 +33,9 @@ def world_info():
 
 
 class ShardPlan:
-    """Layout of one rank's shard.  `neighbours` is the GLOBAL table [W,6] (-1 = none) or None."""
+    """Layout of one rank's shard.  `neighbours` is the GLOBAL table [W,6] (-1 = none), a callable
+    `neighbours(lo, hi) -> [hi-lo, 6]` giving the rows of a voxel range only (DataModel.neighbour_table; a rank then
+    never builds the table of the whole volume), or None."""
 
     def __init__(self, n_vox, rank, world, neighbours=None):
         self.n_global, self.rank, self.world = int(n_vox), rank, world
@@ -42,11 +44,9 @@ class ShardPlan:
         self.halo_lo = self.halo_hi = 0
         self.neighbours_local = None
         if neighbours is not None:
-            nb = np.asarray(neighbours)[self.lo:self.hi]
-            below = nb[(nb >= 0) & (nb < self.lo)]
-            above = nb[nb >= self.hi]
-            self.halo_lo = int(self.lo - below.min()) if below.size else 0
-            self.halo_hi = int(above.max() + 1 - self.hi) if above.size else 0
+            rows = neighbours if callable(neighbours) else (lambda lo, hi: np.asarray(neighbours)[lo:hi])
+            nb = np.asarray(rows(self.lo, self.hi))
+            self.halo_lo, self.halo_hi = ShardPlan._halo(nb, self.lo, self.hi)
             base = self.lo - self.halo_lo
             local = np.where(nb >= 0, nb - base, -1).astype(np.int32)
             table = -np.ones((self.ld, 6), dtype=np.int32)
@@ -56,21 +56,24 @@ class ShardPlan:
         self.prev_halo_hi = self.next_halo_lo = 0
         if world > 1 and neighbours is not None:
             if rank > 0:
-                self.prev_halo_hi = ShardPlan._halo_of(n_vox, rank - 1, world, neighbours)[1]
+                lo_p = shard_bounds(n_vox, rank - 1, world)
+                self.prev_halo_hi = ShardPlan._halo(np.asarray(rows(*lo_p)), *lo_p)[1]
+            else:
+                lo_p = (0, 0)
             if rank < world - 1:
-                self.next_halo_lo = ShardPlan._halo_of(n_vox, rank + 1, world, neighbours)[0]
+                lo_n = shard_bounds(n_vox, rank + 1, world)
+                self.next_halo_lo = ShardPlan._halo(np.asarray(rows(*lo_n)), *lo_n)[0]
+            else:
+                lo_n = (0, 0)
             if self.prev_halo_hi > self.n_own or self.next_halo_lo > self.n_own:
                 raise ValueError("shard of %d voxels is thinner than the neighbouring rank's halo "
                                  "(use fewer GPUs for this volume)" % self.n_own)
-            lo_p = shard_bounds(n_vox, rank - 1, world) if rank > 0 else (0, 0)
-            lo_n = shard_bounds(n_vox, rank + 1, world) if rank < world - 1 else (0, 0)
             if self.halo_lo > lo_p[1] - lo_p[0] or self.halo_hi > lo_n[1] - lo_n[0]:
                 raise ValueError("halo reaches beyond the adjacent rank (use fewer GPUs for this volume)")
 
     @staticmethod
-    def _halo_of(n_vox, rank, world, neighbours):
-        lo, hi = shard_bounds(n_vox, rank, world)
-        nb = np.asarray(neighbours)[lo:hi]
+    def _halo(nb, lo, hi):
+        """(lower, upper) halo sizes of the voxel range [lo, hi) whose neighbour rows are `nb`."""
         below = nb[(nb >= 0) & (nb < lo)]
         above = nb[nb >= hi]
         return (int(lo - below.min()) if below.size else 0, int(above.max() + 1 - hi) if above.size else 0)

@@ -57,18 +57,42 @@ class DataModel(LogBase):
             return data, np.asarray(data.data)
         return None, np.asarray(data)
 
-    def voxel_coords(self):
-        """Integer (x,y,z) of every masked voxel, in voxel order -> [W,3] int32"""
-        idx = np.nonzero(self.mask_flattened)[0]
+    @classmethod
+    def header(cls, shape, n_tpts, mask=None):
+        """A data model that knows the volume's geometry but holds no samples (`data_flattened` is None): for
+        callers whose data already live on the device (bench.py's 10 M-voxel volume) and only need the plugin's
+        option handling, time points and neighbour structure."""
+        self = cls.__new__(cls)
+        LogBase.__init__(self)
+        self.nii, self.data_vol = None, None
+        self.shape = [int(x) for x in shape]
+        self.n_tpts = int(n_tpts)
+        self.mask_vol = np.ones(self.shape, dtype=np.int32) if mask is None else np.asarray(mask)
+        self.mask_flattened = self.mask_vol.reshape(-1) > 0
+        self.data_flattened = None
+        self.n_unmasked_voxels = self.n_nodes = int(self.mask_flattened.sum())
+        self.node_labels = [(slice(0, self.n_nodes), "GM")]
+        self.affine = np.eye(4)
+        return self
+
+    def voxel_coords(self, lo=None, hi=None):
+        """Integer (x,y,z) of the masked voxels [lo, hi) (default all), in voxel order -> [n,3] int32"""
+        if getattr(self, "_vox_index", None) is None:
+            self._vox_index = np.nonzero(self.mask_flattened)[0]
+        idx = self._vox_index[slice(lo, hi)]
         X, Y, Z = self.shape
         return np.stack([idx // (Y * Z), (idx // Z) % Y, idx % Z], axis=1).astype(np.int32)
 
-    def neighbour_table(self):
-        """6-connected neighbours inside the mask -> [W,6] int32 voxel indices (-x,+x,-y,+y,-z,+z), -1 = none.
-        The Laplacian structure of the spatial ("M") prior."""
-        coords = self.voxel_coords()
-        lut = -np.ones(self.shape, dtype=np.int64)
-        lut[coords[:, 0], coords[:, 1], coords[:, 2]] = np.arange(len(coords))
+    def neighbour_table(self, lo=None, hi=None):
+        """6-connected neighbours inside the mask of the voxels [lo, hi) (default all) -> [n,6] int32 GLOBAL voxel
+        indices (-x,+x,-y,+y,-z,+z), -1 = none.  The Laplacian structure of the spatial ("M") prior (SURVEY
+        Appendix A.5); a rank of a sharded fit asks for its own range only."""
+        coords = self.voxel_coords(lo, hi)
+        if getattr(self, "_vox_lut", None) is None:
+            lut = -np.ones(int(np.prod(self.shape)), dtype=np.int32)
+            lut[self.mask_flattened] = np.arange(self.n_nodes, dtype=np.int32)
+            self._vox_lut = lut.reshape(self.shape)
+        lut = self._vox_lut
         out = -np.ones((len(coords), 6), dtype=np.int32)
         k = 0
         for axis in range(3):

@@ -64,7 +64,7 @@ class SvbFit(LogBase):
         neighbours = None
         halo = (0, 0)
         self.plan = ShardPlan(self.data_model.n_nodes, self.rank, self.world,
-                              self.data_model.neighbour_table() if "M" in prior_types else None)
+                              self.data_model.neighbour_table if "M" in prior_types else None)
         if (self.lo, self.hi) != (self.plan.lo, self.plan.hi):           # caller overrode the shard (bench.py)
             self.plan = ShardPlan(hi - lo, 0, 1, None)
             self.plan.lo, self.plan.hi = lo, hi
@@ -108,22 +108,15 @@ class SvbFit(LogBase):
             means.append(np.broadcast_to(np.asarray(mean, dtype=np.float32), (hi - lo,)))
             variances.append(np.broadcast_to(np.asarray(var, dtype=np.float32), (hi - lo,)))
         self.fused.set_posterior(means, variances)
-        if self.world > 1 and "M" in prior_types:
-            self.fused.halo_exchange = plan.exchange_halo
-            self.fused.reduce_fn = ShardPlan.allreduce_sum
-            plan.exchange_halo(self.fused.state)
-            # "peer": halo stores and the log-ak all-reduce over NVLink peer memory, iteration replayed as a CUDA
-            # graph; "peer+nccl": same, the all-reduce by NCCL; "nccl": send/recv halo exchange on a side stream
+        if "M" in prior_types:
+            # "peer": next-iteration samples of boundary voxels stored straight into the neighbours' halos and the
+            # log-ak all-reduce over peer-memory mailboxes, both inside the step kernel (one launch per iteration,
+            # replayed as a CUDA graph); "peer+nccl": the all-reduce by NCCL; "nccl": send/recv of the halo samples
             mode = kwargs.get("halo_mode", "peer")
-            if mode == "none":
-                pass
-            elif mode in ("peer", "peer+nccl"):
-                self.fused.share_state_with_neighbours(plan, ak_reduce="peer" if mode == "peer" else "nccl")
+            if self.world > 1:
+                self.fused.shard(plan, halo_mode=mode, reduce_fn=ShardPlan.allreduce_sum)
+            if kwargs.get("use_graph", True) and (self.world == 1 or mode in ("peer", "peer+nccl")):
                 self.fused.enable_graph()
-            elif kwargs.get("overlap_halo", True):
-                self.fused.enable_overlap(plan)
-        elif "M" in prior_types and kwargs.get("use_graph", True):
-            self.fused.enable_graph()
 
     # ------------------------------------------------------------------
     def train(self, tpts, data, batch_size=None, epochs=100, learning_rate=0.1, sample_size=None, display_step=1,
@@ -161,6 +154,8 @@ class SvbFit(LogBase):
                 k = min(fuse, n_batches - done)
                 acc = acc + f.step(k).sum()
                 done += k
+            if f.mrf and self.world > 1 and (epoch + 1) % 64 == 0:
+                f.check_peers()                                 # a lost rank surfaces here, not at teardown
             if not want_vc:
                 cost_dev[epoch + 1] = acc / n_batches          # mean of the batch costs (no extra launch)
             record(epoch + 1)
@@ -168,7 +163,8 @@ class SvbFit(LogBase):
                 # one host sync per displayed epoch; keep display_step large for big fits
                 mc = float(cost_dev[epoch + 1]) / f.n_vox
                 kwargs["log_stream"].write(" - Epoch %04d: mean cost=%f (shard of %i voxels)\n" % (epoch + 1, mc, f.n_vox))
-        f.finish() if hasattr(f, "finish") else None
+        if f.mrf:
+            f.check_peers()
         torch.cuda.synchronize()
         self.runtime = time.time() - t0
         total = cost_dev.clone()

@@ -145,7 +145,7 @@ class Backend:
 
     def engine_desc(self, spec, state, data, tpts, eps=None, *, n_batch=None, t_row0=0, t_row_stride=1, seed=1,
                     neighbours=None, log_ak=None, w_begin=0, n_vox=None, vox_offset=0, n_vox_global=None,
-                    grad_scale=None, ti=None, zoff=None, state_out=False):
+                    grad_scale=None, ti=None, zoff=None, state_out=False, next_samples=False):
         """state [n_state,ld], data/tpts [T,ld], eps [P',S,ld] numpy (float64 ok) -> (Engine, buffers dict)"""
         ld = state.shape[1]
         e = L.Engine()
@@ -176,6 +176,7 @@ class Backend:
         bufs["log_ak"] = self.put(log_ak) if log_ak is not None else None
         bufs["ak_grad"] = self.zeros((4,), np.float64) if log_ak is not None else None
         bufs["sp"] = self.zeros((len(log_ak), spec.n_samples, ld)) if log_ak is not None else None
+        bufs["sp_next"] = self.zeros((len(log_ak), spec.n_samples, ld)) if (log_ak is not None and next_samples) else None
         bufs["state_out"] = self.put(state) if state_out else None
         e.state = self.ptr(bufs["state"])
         e.state_out = self.ptr(bufs["state_out"])
@@ -188,6 +189,7 @@ class Backend:
         e.seed = seed
         e.neighbours = self.ptr(bufs["nbr"])
         e.spatial_samples = self.ptr(bufs["sp"])
+        e.spatial_samples_out = self.ptr(bufs["sp_next"])
         e.log_ak = self.ptr(bufs["log_ak"])
         e.ak_grad = self.ptr(bufs["ak_grad"])
         return e, bufs

@@ -54,6 +54,7 @@ static int run_step(const svbasl_model *md, const svbasl_engine *e, const svbasl
             if (ad) {
                 if (vs.grads_finite() && c == c) vs.adam_update(*e, *ad, ad->lr_t[step], w, it == n_iters - 1, ad->m + w, ad->v + w, e->ld, ad->m + w, ad->v + w, e->ld);
                 else { if (it == n_iters - 1) vs.store_state(*e, w); c = 0.0f; }
+                if (FL != 1 && it == n_iters - 1 && e->spatial_samples_out) vs.store_next_samples(*e, ec, w, step + 1);
             }
             if (cost_sum) cost_sum[it] += c;
             if (ak_grad)

@@ -121,14 +121,41 @@ def test_spatial_prior_requirements_are_checked(lib):
     e.latent = L.LATENT_ANALYTIC
     assert lib.svbasl_elbo_grad(C.byref(m), C.byref(e), 0, None, None, None, None) < 0
     assert b"sample-based latent loss" in lib.svbasl_last_error()
-    # an update with a spatial prior needs a separate output buffer and one iteration per launch
+    # an update with a spatial prior is one iteration per launch
     e.latent = L.LATENT_NUMERIC
     e.neighbours = e.log_ak = e.spatial_samples = 0x1000
     ad = L.Adam()
     ad.m = ad.v = ad.lr_t = 0x1000
     ad.n_iters, ad.n_batches = 2, 1
     assert lib.svbasl_step(C.byref(m), C.byref(e), C.byref(ad), None, None, None) < 0
-    assert b"spatial priors need n_iters == 1" in lib.svbasl_last_error()
+    assert b"n_iters must be 1" in lib.svbasl_last_error()
+    # next-iteration samples: a second buffer and the in-kernel draws
+    ad.n_iters = 1
+    e.spatial_samples_out = e.spatial_samples
+    assert lib.svbasl_step(C.byref(m), C.byref(e), C.byref(ad), None, None, None) < 0
+    assert b"spatial_samples_out needs" in lib.svbasl_last_error()
+    e.spatial_samples_out = 0x2000
+    e.eps = 0x3000
+    assert lib.svbasl_step(C.byref(m), C.byref(e), C.byref(ad), None, None, None) < 0
+    assert b"spatial_samples_out needs" in lib.svbasl_last_error()
+    e.eps = None
+    # peer pointers must name the first / last owned voxels of the launch
+    e.peer_lo, e.peer_lo_first, e.peer_lo_count = 0x4000, e.w_begin + 1, 2
+    assert lib.svbasl_step(C.byref(m), C.byref(e), C.byref(ad), None, None, None) < 0
+    assert b"first / last owned voxels" in lib.svbasl_last_error()
+    e.peer_lo = None
+    # fused hyper tail: needs the device counter shared with the engine
+    hy = L.Hyper()
+    hy.log_ak, hy.m, hy.v, hy.lr_t, hy.done_ctas, hy.step_dev = e.log_ak, 0x1000, 0x1000, 0x1000, 0x1000, 0x5000
+    hy.n_spatial, hy.world = 1, 1
+    e.ak_grad = 0x1000
+    assert lib.svbasl_step_spatial(C.byref(m), C.byref(e), C.byref(ad), C.byref(hy), None, None, None) < 0
+    assert b"bad svbasl_hyper descriptor" in lib.svbasl_last_error()
+    e.step_dev = 0x5000
+    hy.world, hy.status = 2, 0x1000
+    hy.mailboxes[0] = 0x6000
+    assert lib.svbasl_step_spatial(C.byref(m), C.byref(e), C.byref(ad), C.byref(hy), None, None, None) < 0
+    assert b"mailbox of rank 1 is NULL" in lib.svbasl_last_error()
 
 
 def test_null_and_range_checks_of_the_small_entry_points(lib):
@@ -144,7 +171,7 @@ def test_null_and_range_checks_of_the_small_entry_points(lib):
     assert lib.svbasl_mailbox_bytes(8) == 2 * 8 * 40 and lib.svbasl_mailbox_bytes(0) == 0
     assert lib.svbasl_shared_alloc(0, None, None) < 0
     assert lib.svbasl_sample_spatial(None, 0, 0, None, None) < 0
-    assert lib.svbasl_abi_version() == 1
+    assert lib.svbasl_abi_version() == 2
 
 
 def test_plugin_option_errors_match_the_reference_texts():

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in _declared():
         assert hasattr(lib, name), name
     lib.svbasl_abi_version.restype = ctypes.c_int
-    assert lib.svbasl_abi_version() == 1
+    assert lib.svbasl_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():
@@ -43,7 +43,9 @@ int main(void) {
   printf("%zu %zu %zu ", sizeof(svbasl_model), sizeof(svbasl_engine), sizeof(svbasl_adam));
   printf("%zu %zu %zu %zu ", offsetof(svbasl_model, pvgm), offsetof(svbasl_model, nn_weights),
          offsetof(svbasl_engine, state), offsetof(svbasl_engine, ak_grad));
-  printf("%zu %zu\n", offsetof(svbasl_engine, prior_var), offsetof(svbasl_adam, step0));
+  printf("%zu %zu ", offsetof(svbasl_engine, prior_var), offsetof(svbasl_adam, step0));
+  printf("%zu %zu %zu %zu %zu\n", sizeof(svbasl_hyper), offsetof(svbasl_hyper, mailboxes), offsetof(svbasl_hyper, status),
+         offsetof(svbasl_engine, peer_hi_count), offsetof(svbasl_engine, cost_sum_scalar));
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
@@ -52,9 +54,10 @@ int main(void) {
         exe = os.path.join(d, "l")
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
-    M, E, A = _lib.Model, _lib.Engine, _lib.Adam
+    M, E, A, Hy = _lib.Model, _lib.Engine, _lib.Adam, _lib.Hyper
     want = [ctypes.sizeof(M), ctypes.sizeof(E), ctypes.sizeof(A), M.pvgm.offset, M.nn_weights.offset, E.state.offset,
-            E.ak_grad.offset, E.prior_var.offset, A.step0.offset]
+            E.ak_grad.offset, E.prior_var.offset, A.step0.offset, ctypes.sizeof(Hy), Hy.mailboxes.offset,
+            Hy.status.offset, E.peer_hi_count.offset, E.cost_sum_scalar.offset]
     assert got == want
 
 

@@ -344,3 +344,58 @@ def test_nn_trainer_reduces_loss_and_round_trips_weights(tmp_path):
     assert shapes == [(2, 10), (1, 10), (10, 10), (1, 10), (10, 1), (1, 1)]
     again = AslNNModel(dm, train_load=str(tmp_path / "w"), **opts)
     np.testing.assert_array_equal(again._ievaluate_nn(x_test), model._ievaluate_nn(x_test))
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_spatial_iteration_follows_the_oracle(use_graph, record_error):
+    """One launch per iteration with an MRF prior (svbasl_step_spatial: neighbour samples read from the buffer the
+    previous launch wrote, next-iteration samples written after the Adam update, log-ak gradient reduced and stepped
+    by the last CTA, iteration counter on the device; eager and as a CUDA-graph replay) against the oracle's fit with
+    a trainable log ak (autograd through the Laplacian term) on identical draws."""
+    from svb import DataModel
+    from svb_models_asl import AslRestModel
+    from svb_models_asl_b200.svbcompat.fit import SvbFit
+    rng = np.random.default_rng(17)
+    shape = (6, 5, 4)
+    vol, _f, _d = _sim_volume(shape, rng, noise=1.0, t1b=1.65)
+    dm = DataModel(vol)
+    over = {"ftiss": {"prior_type": "M"}}
+    model = AslRestModel(dm, tau=1.8, casl=True, plds=PLDS, repeats=[1], param_overrides=over)
+    fit = SvbFit(dm, model)
+    fit._setup(model.tpts(), dm.data_flattened, None, 10, 0.05, epochs=16, force_num_latent_loss=True, use_graph=False,
+               ak=0.3, seed=5, param_overrides=over)
+    f = fit.fused
+    W, n_it = dm.n_nodes, 5
+    cfg = om.AslConfig(casl=True, tau=1.8, t1b=1.65)
+    spec = H.aslrest_spec(cfg, mrf=(0,))
+    e = f.engine_desc()
+    assert [e.prior_type[i] for i in range(3)] == [2, 0, 0]
+    np.testing.assert_allclose([e.prior_mean[i] for i in range(3)], [float(np.mean(x)) for x in spec.prior_mean], rtol=1e-6)
+    np.testing.assert_allclose([e.prior_var[i] for i in range(3)], spec.prior_var, rtol=1e-6)
+    prob = H.synth_problem(cfg, spec, W, rng)                      # only its random posterior state is used
+    state0 = prob["state"].astype(np.float32)
+    f.state.copy_(torch.as_tensor(state0, device=f.dev))
+    f.sp_valid = False
+    eps_all = [f.fill_eps(it).cpu().numpy() for it in range(n_it)]
+    data = dm.data_flattened.T.astype(np.float64)
+    tp = np.broadcast_to(model.tpts(), dm.data_flattened.shape).T.astype(np.float64)
+    ost, ohy = eng.fit(spec, torch.as_tensor(state0.astype(np.float64)), torch.tensor([math.log(0.3)], dtype=torch.float64),
+                       torch.as_tensor(data), torch.as_tensor(tp), n_it, 6, 0.05,
+                       lambda it: torch.as_tensor(eps_all[it], dtype=torch.float64),
+                       neighbours=torch.as_tensor(dm.neighbour_table().astype(np.int64)))
+    if use_graph:
+        f.enable_graph()
+    for _ in range(n_it):
+        f.step()
+    f.check_peers()
+    assert int(f.step_dev.item()) == n_it and f.step_count == n_it
+    st = f.state.cpu().numpy()
+    err = H.rel_err(st, ost.numpy())[:, 0]
+    lak_err = abs(float(f.log_ak[0]) - float(ohy[0])) / abs(float(ohy[0]))
+    record_error("fused_spatial_vs_oracle/%s" % ("graph" if use_graph else "eager"), state_rows_rel=float(err.max()),
+                 log_ak_rel=float(lak_err))
+    assert np.abs(ost.numpy() - state0).max() > 0.05 and abs(float(ohy[0]) - math.log(0.3)) > 0.05
+    assert err.max() <= 1e-4, err
+    assert lak_err <= 1e-4, lak_err
+    costs = f.cost_hist[:n_it].cpu().numpy()
+    assert np.isfinite(costs).all() and (costs != 0).all()

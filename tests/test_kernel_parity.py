@@ -478,7 +478,12 @@ def test_lean_production_flavour_equals_generic(be):
             assert nanc == 0 and np.isfinite(csum).all()
         finals.append(be.get(bufs["state"]))
     assert np.abs(finals[0] - prob["state"]).max() > 1e-2          # four steps moved the posterior
-    np.testing.assert_allclose(finals[1], finals[0], rtol=1e-6, atol=1e-7)
+    # two compilations of the same source contract multiply-adds differently; Adam's m/sqrt(v) amplifies that last-bit
+    # noise where a gradient is near zero (the arterial arrival time, see the oracle test below): a few values in a
+    # thousand differ by up to 5e-6 absolute on the GPU, the rest to the last bits
+    rel = H.rel_err(finals[1], finals[0])[:, 0]
+    assert rel.max() <= 1e-4, rel
+    assert np.mean(np.abs(finals[1] - finals[0]) > 1e-6 * np.maximum(np.abs(finals[0]), 1e-1)) < 0.02
 
 
 def test_lean_production_step_follows_the_oracle(be, record_error):
@@ -553,6 +558,48 @@ def test_spatial_production_flavour_equals_generic(be, mrf):
     np.testing.assert_allclose(out[1][0], out[0][0], rtol=2e-6, atol=2e-7)
     np.testing.assert_allclose(out[1][1], out[0][1], rtol=1e-5)
     np.testing.assert_allclose(out[1][2], out[0][2], rtol=1e-6)
+
+
+@pytest.mark.parametrize("mrf", [(0,), (0, 1)])
+def test_step_writes_the_next_iterations_neighbour_samples(be, mrf):
+    """A fused spatial step also produces theta(step+1) of every voxel's spatial parameters from its UPDATED state
+    (svbasl_engine.spatial_samples_out) - bit for bit what the pre-pass kernel (svbasl_sample_spatial) computes from
+    that state for step+1 - so the next iteration needs no pre-pass; and a second iteration that reads them ends
+    where the pre-pass route ends."""
+    rng = np.random.default_rng(43)
+    shape = (5, 4, 6)
+    coords, nb = _grid_neighbours(shape)
+    W = len(coords)
+    cfg = om.AslConfig(casl=True, tau=1.8, t1b=1.65)
+    spec = H.aslrest_spec(cfg, mrf=mrf)
+    prob = H.synth_problem(cfg, spec, W, rng)
+    log_ak = np.asarray([-1.0, 0.3][:len(mrf)], dtype=np.float32)
+    m = be.model_desc(cfg)
+    finals = []
+    for route in ("fused", "prepass"):
+        e, bufs = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], None, seed=5, neighbours=nb.T.copy(),
+                                 log_ak=log_ak, next_samples=(route == "fused"))
+        be.sample_spatial(e, bufs, step=7)
+        ad, _ab = be.adam_desc(spec.n_state, W, 0.05, 16, step0=7)
+        csum, nanc = be.step(m, e, ad, nbt=206)
+        assert nanc == 0 and np.isfinite(csum).all()
+        if route == "fused":
+            nxt = be.get(bufs["sp_next"])
+            # the pre-pass on the updated state for step 8 gives the same samples
+            e2 = e
+            e2.spatial_samples_out = None
+            ref = be.sample_spatial(e2, bufs, step=8)
+            np.testing.assert_array_equal(nxt, ref)
+            e.spatial_samples = be.ptr(bufs["sp_next"])
+            e.spatial_samples_out = be.ptr(bufs["sp"])
+        else:
+            be.sample_spatial(e, bufs, step=8)
+        ad.step0 = 8
+        csum, nanc = be.step(m, e, ad, nbt=206)
+        assert nanc == 0 and np.isfinite(csum).all()
+        finals.append((be.get(bufs["state"]), be.get(bufs["ak_grad"])[:len(mrf)].copy(), csum))
+    np.testing.assert_array_equal(finals[0][0], finals[1][0])
+    np.testing.assert_array_equal(finals[0][1], finals[1][1])
 
 
 @pytest.mark.parametrize("casl", [True, False])
