@@ -128,7 +128,8 @@ typedef struct svbasl_engine {
     const float *zoff;             /* [ld] slice offset z*slicedt, or NULL (= 0) */
     int32_t t_row0, t_row_stride;
     /* random draws: eps [P'][S][ld] read from memory when non-NULL (parity mode, the reference's
-     * tf.random_normal is not reproducible); otherwise Philox4x32-10 keyed on (seed, step, global voxel) */
+     * tf.random_normal is not reproducible); otherwise Philox2x32-10 keyed on (seed, step, global voxel), one call
+     * = row j of samples 2k and 2k+1 (csrc/philox.h; svbasl_fill_eps writes the same stream out) */
     const float *eps;
     uint64_t seed;
     /* spatial prior ("M"): neighbour table [6][ld] of LOCAL voxel indices, -1 = none.  The local arrays

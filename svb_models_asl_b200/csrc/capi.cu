@@ -124,12 +124,13 @@ __global__ void fill_eps_kernel(float *eps, int64_t n_vox, int64_t ld, int64_t v
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_vox) return;
     const uint32_t key = rng_key(seed, step);
-    for (int s = 0; s < n_samples; ++s) {
-        for (int k = 0; 2 * k < n_par; ++k) {
+    // row j of samples s, s+1 = one Philox call (philox.h: stream_pair)
+    for (int j = 0; j < n_par; ++j) {
+        for (int s = 0; s < n_samples; s += 2) {
             float n0, n1;
-            normal2(key, vox_offset + w, s, k, n0, n1);
-            eps[((int64_t)(2 * k) * n_samples + s) * ld + w] = n0;
-            if (2 * k + 1 < n_par) eps[((int64_t)(2 * k + 1) * n_samples + s) * ld + w] = n1;
+            normal_pair(key, vox_offset + w, stream_pair(j, s, n_samples), n0, n1);
+            eps[((int64_t)j * n_samples + s) * ld + w] = n0;
+            if (s + 1 < n_samples) eps[((int64_t)j * n_samples + s + 1) * ld + w] = n1;
         }
     }
 }

@@ -313,8 +313,8 @@ static __global__ void __launch_bounds__(kBlock) spatial_sample_kernel(const __g
     const int64_t ld = a.e.ld;
     int p_first = 0;
     if (!a.e.eps) {
-        // Parameters 0 and 1 (ftiss, delttiss: the usual spatial ones) depend on the first pair of draws only:
-        // one Philox call per sample serves both, the row of L is read once (same arithmetic as sample_theta).
+        // Parameters 0 and 1 (ftiss, delttiss: the usual spatial ones): one Philox call per row serves two samples;
+        // the row of L is read once (same arithmetic, term by term, as sample_theta / store_next_samples).
         const int s0 = a.ec.sp_slot[0], s1 = n > 1 ? a.ec.sp_slot[1] : -1;
         p_first = n > 1 ? 2 : 1;
         if (s0 >= 0 || s1 >= 0) {
@@ -328,11 +328,19 @@ static __global__ void __launch_bounds__(kBlock) spatial_sample_kernel(const __g
             }
             float *o0 = a.out + (int64_t)(s0 >= 0 ? s0 : 0) * S * ld + u;
             float *o1 = a.out + (int64_t)(s1 >= 0 ? s1 : 0) * S * ld + u;
-            for (int s = 0; s < S; ++s) {
-                float e0, e1;
-                normal2(key, a.e.vox_offset + u, s, 0, e0, e1);
-                if (s0 >= 0) o0[(int64_t)s * ld] = mu0 + sd0 * e0;
-                if (s1 >= 0) o1[(int64_t)s * ld] = (mu1 + od10 * e0) + sd1 * e1;
+            for (int s = 0; s < S; s += 2) {
+                float e0a, e0b, e1a = 0.0f, e1b = 0.0f;
+                normal_pair(key, a.e.vox_offset + u, stream_pair(0, s, S), e0a, e0b);
+                if (s1 >= 0) normal_pair(key, a.e.vox_offset + u, stream_pair(1, s, S), e1a, e1b);
+                const bool two = s + 1 < S;
+                if (s0 >= 0) {
+                    o0[(int64_t)s * ld] = mu0 + sd0 * e0a;
+                    if (two) o0[(int64_t)(s + 1) * ld] = mu0 + sd0 * e0b;
+                }
+                if (s1 >= 0) {
+                    o1[(int64_t)s * ld] = (mu1 + od10 * e0a) + sd1 * e1a;
+                    if (two) o1[(int64_t)(s + 1) * ld] = (mu1 + od10 * e0b) + sd1 * e1b;
+                }
             }
         }
     }

@@ -3,10 +3,9 @@
 // The reference draws eps with tf.random_normal inside svb (sample = mean +
 // chol @ eps, eps [W,P',S]); that stream is not reproducible outside TensorFlow, so parity runs take
 // eps from memory and production runs generate it here.  Philox2x32-10 (Salmon et al. 2011, Random123):
-// counter = (global voxel id, sample index | parameter pair), key = mix(seed, step).  One call yields the
-// draws of parameter rows 2k and 2k+1 for one sample (a Box-Muller pair), so nothing has to be cached across
-// samples, and a voxel's stream depends only on (seed, step, global voxel id): results do not depend on how
-// voxels are sharded over GPUs.
+// counter = (global voxel id, pair number), key = mix(seed, step).  One call yields a Box-Muller pair = two
+// consecutive normals of the voxel's stream for that step (numbering below); a voxel's stream depends only on
+// (seed, step, global voxel id): results do not depend on how voxels are sharded over GPUs.
 #pragma once
 #include "compat.h"
 
@@ -34,11 +33,14 @@ SVB_HD uint32_t rng_key(uint64_t seed, int64_t step) {
 // uniform in (0,1): 24 random bits, never 0 or 1
 SVB_HD float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f + 2.98023223876953125e-08f; }
 
-// two standard normals for (voxel, sample s, parameter pair k): rows 2k and 2k+1
-SVB_HD void normal2(uint32_t key, int64_t vox_global, int s, int pair, float &n0, float &n1) {
+// The stream of one (voxel, step): normals numbered q = j*S2 + s (posterior row j, sample s; S2 = S rounded up to
+// even).  Normals 2p and 2p+1 are the Box-Muller pair of ONE Philox call with counter (global voxel, p): a call
+// serves the SAME row of two consecutive samples.  The sample loop therefore draws all N rows for samples s and s+1
+// together on even s (N calls, N/2 per sample whatever N is), and one row of all S samples - what a neighbour needs
+// of a spatially regularised parameter - costs S/2 calls.
+SVB_HD void normal_pair(uint32_t key, int64_t vox_global, int pair, float &n0, float &n1) {
     uint32_t a, b;
-    philox2x32_10((uint32_t)vox_global, ((uint32_t)s << 4 | (uint32_t)pair) ^ ((uint32_t)((uint64_t)vox_global >> 32) << 24),
-                  key, a, b);
+    philox2x32_10((uint32_t)vox_global, (uint32_t)pair ^ ((uint32_t)((uint64_t)vox_global >> 32) << 24), key, a, b);
     const float rad = fsqrt(-2.0f * flog(u01(a)));
     float sn, cs;
     fsincos2pi(u01(b), &sn, &cs);
@@ -46,15 +48,25 @@ SVB_HD void normal2(uint32_t key, int64_t vox_global, int s, int pair, float &n0
     n1 = rad * sn;
 }
 
-// all N draws of one sample
+SVB_HD int stream_pair(int j, int s, int S) { return (j * ((S + 1) >> 1)) + (s >> 1); }
+
+// one normal: row j of sample s (slow path: single rows, tests)
+SVB_HD float normal_at(uint32_t key, int64_t vox_global, int j, int s, int S) {
+    float n0, n1;
+    normal_pair(key, vox_global, stream_pair(j, s, S), n0, n1);
+    return (s & 1) ? n1 : n0;
+}
+
+// All N draws of sample s inside a loop over s = 0, 1, 2, ...: an even sample draws the pairs and leaves the second
+// halves in `spare` for the odd sample that follows.  The branch on s is uniform across the warp.
 template <int N>
-SVB_HD void normal_row(uint32_t key, int64_t vox_global, int s, float *eps) {
+SVB_HD void normal_row(uint32_t key, int64_t vox_global, int s, int S, float *eps, float *spare) {
+    if ((s & 1) == 0) {
 #pragma unroll
-    for (int k = 0; k < (N + 1) / 2; ++k) {
-        float n0, n1;
-        normal2(key, vox_global, s, k, n0, n1);
-        eps[2 * k] = n0;
-        if (2 * k + 1 < N) eps[2 * k + 1] = n1;
+        for (int j = 0; j < N; ++j) normal_pair(key, vox_global, stream_pair(j, s, S), eps[j], spare[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) eps[j] = spare[j];
     }
 }
 

@@ -98,18 +98,10 @@ SVB_HD float sample_theta(const svbasl_engine &e, uint32_t key, int64_t u, int p
     const int n = e.n_par;
     const float *st = e.state + u;
     float th = st[(int64_t)p * e.ld];
-    for (int k = 0; 2 * k <= p; ++k) {
-        float e0, e1;
-        if (e.eps) {
-            e0 = e.eps[((int64_t)(2 * k) * e.n_samples + s) * e.ld + u];
-            e1 = (2 * k + 1 <= p) ? e.eps[((int64_t)(2 * k + 1) * e.n_samples + s) * e.ld + u] : 0.0f;
-        } else {
-            normal2(key, e.vox_offset + u, s, k, e0, e1);
-        }
-        const int j0 = 2 * k, j1 = 2 * k + 1;
-        th += (j0 == p ? fexp(0.5f * st[(int64_t)(n + p) * e.ld]) : st[(int64_t)(2 * n + stri(p, j0)) * e.ld]) * e0;
-        if (j1 <= p)
-            th += (j1 == p ? fexp(0.5f * st[(int64_t)(n + p) * e.ld]) : st[(int64_t)(2 * n + stri(p, j1)) * e.ld]) * e1;
+    for (int j = 0; j <= p; ++j) {
+        const float ej = e.eps ? e.eps[((int64_t)j * e.n_samples + s) * e.ld + u]
+                               : normal_at(key, e.vox_offset + u, j, s, e.n_samples);
+        th += (j == p ? fexp(0.5f * st[(int64_t)(n + p) * e.ld]) : st[(int64_t)(2 * n + stri(p, j)) * e.ld]) * ej;
     }
     return th;
 }
@@ -209,13 +201,16 @@ struct VoxelStep {
         for (int k = 0; k < NT; ++k) a_L[k] = 0.0f;
         float cost = 0.0f;
 
+        float spare[N];                                // second halves of the Box-Muller pairs: the next sample's draws
+#pragma unroll
+        for (int j = 0; j < N; ++j) spare[j] = 0.0f;
         for (int s = 0; s < S; ++s) {
             float eps[N];
             if (eps_mem) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) eps[j] = e.eps[((int64_t)j * S + s) * e.ld + w];
             } else {
-                normal_row<N>(key, e.vox_offset + w, s, eps);
+                normal_row<N>(key, e.vox_offset + w, s, S, eps, spare);
             }
             float th[N];
 #pragma unroll
@@ -457,22 +452,28 @@ struct VoxelStep {
                         ? e.peer_lo + (w + e.peer_lo_shift) : nullptr;
         float *hi = (e.peer_hi && w >= e.peer_hi_first && w < e.peer_hi_first + e.peer_hi_count)
                         ? e.peer_hi + (w + e.peer_hi_shift) : nullptr;
-        for (int s = 0; s < S; ++s) {
-            float eps[N + 1];
+        for (int s0 = 0; s0 < S; s0 += 2) {                  // two samples per Philox call and row
+            float ea[N], eb[N];
 #pragma unroll
-            for (int k = 0; k < (N + 1) / 2; ++k)
-                if (2 * k <= pmax) normal2(key, e.vox_offset + w, s, k, eps[2 * k], eps[2 * k + 1]);
+            for (int j = 0; j < N; ++j)
+                if (j <= pmax) normal_pair(key, e.vox_offset + w, stream_pair(j, s0, S), ea[j], eb[j]);
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 if (e.prior_type[i] != SVBASL_PRIOR_MRF) continue;
-                float th = mu[i];
+                float tha = mu[i], thb = mu[i];
 #pragma unroll
-                for (int j = 0; j < i; ++j) th += od[stri(i, j)] * eps[j];
-                th += sdn[i] * eps[i];
-                const int64_t row = (int64_t)ec.sp_slot[i] * S + s;
-                own[row * e.ld] = th;
-                if (lo) lo[row * e.peer_lo_ld] = th;
-                if (hi) hi[row * e.peer_hi_ld] = th;
+                for (int j = 0; j < i; ++j) { tha += od[stri(i, j)] * ea[j]; thb += od[stri(i, j)] * eb[j]; }
+                tha += sdn[i] * ea[i];
+                thb += sdn[i] * eb[i];
+                const int64_t row = (int64_t)ec.sp_slot[i] * S + s0;
+                own[row * e.ld] = tha;
+                if (lo) lo[row * e.peer_lo_ld] = tha;
+                if (hi) hi[row * e.peer_hi_ld] = tha;
+                if (s0 + 1 < S) {
+                    own[(row + 1) * e.ld] = thb;
+                    if (lo) lo[(row + 1) * e.peer_lo_ld] = thb;
+                    if (hi) hi[(row + 1) * e.peer_hi_ld] = thb;
+                }
             }
         }
 #if defined(__CUDA_ARCH__)

@@ -7,6 +7,7 @@ raise.
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -228,6 +229,10 @@ class FusedSvb:
         self.nan_count = z(1, dt=torch.int64)
         self.neighbours = device_array(neighbours, self.dev, torch.int32) if neighbours is not None else None
         self.eps = None
+        # how a spatial iteration is launched (measurement switch, SVBASL_SPATIAL_FLOW): "fused" = one launch, next
+        # samples + hyper tail in the step kernel; "separate_tail" = step kernel + hyper-step launch; "prepass" =
+        # round-1 flow, pre-pass kernel + step kernel + hyper-step launch (single GPU / NCCL modes only)
+        self.spatial_flow = os.environ.get("SVBASL_SPATIAL_FLOW", "fused")
         self.plan = None            # ShardPlan of a spatial prior sharded over several ranks
         self.halo_mode = None
         self.reduce_fn = None       # sums a small tensor over all ranks in place (NCCL / gloo)
@@ -380,17 +385,31 @@ class FusedSvb:
         e = self.engine_desc(for_step=True)
         ad = self.adam_desc(1)
         mode = self.halo_mode if (self.plan is not None and self.plan.world > 1) else None
-        fused_tail = mode in (None, "peer")
+        fused_tail = mode in (None, "peer") and self.spatial_flow == "fused"
+        if self.spatial_flow == "prepass" and mode in (None, "nccl"):
+            e.spatial_samples_out = None                        # samples of THIS iteration by the pre-pass kernel
+            if mode == "nccl":
+                self.plan.exchange_halo(self.state)
+            L.check(self.lib.svbasl_sample_spatial(C.byref(e), self.ld, 0, self.sp_bufs[self.sp_cur].data_ptr(), _stream_ptr()))
         hy = self.hyper_desc() if fused_tail else None
         L.check(self.lib.svbasl_step_spatial(C.byref(self.mdesc), C.byref(e), C.byref(ad),
                                              C.byref(hy) if hy is not None else None, self.cost_hist.data_ptr(),
                                              self.nan_count.data_ptr(), _stream_ptr()))
         if fused_tail:
             return
-        if mode == "nccl":
+        if mode == "peer":                                     # separate_tail: the mailbox all-reduce as its own launch
+            hy = self.hyper_desc()
+            L.check(self.lib.svbasl_hyper_step_peers(
+                self.log_ak.data_ptr(), self.ak_m.data_ptr(), self.ak_v.data_ptr(), self.ak_grad.data_ptr(),
+                len(self.mrf), 1.0 / self.n_vox_global, self.lr_t.data_ptr(), self.step_dev.data_ptr(), self.b1, self.b2,
+                self.adam_eps, self.plan.rank, self.plan.world, (C.c_void_p * self.plan.world)(*self._mail_ptrs),
+                self.peer_status.data_ptr(), _stream_ptr()))
+            return
+        if mode == "nccl" and self.spatial_flow != "prepass":
             nxt = self.sp_bufs[1 - self.sp_cur]
             self.plan.exchange_halo(nxt.view(-1, self.ld))     # ncclSend/Recv of the boundary voxels' next samples
-        self.reduce_fn(self.ak_grad)                           # NCCL all-reduce (also orders the peer stores)
+        if mode is not None:
+            self.reduce_fn(self.ak_grad)                       # NCCL all-reduce (also orders the peer stores)
         L.check(self.lib.svbasl_hyper_step_dev(self.log_ak.data_ptr(), self.ak_m.data_ptr(), self.ak_v.data_ptr(),
                                                self.ak_grad.data_ptr(), len(self.mrf), 1.0 / self.n_vox_global,
                                                self.lr_t.data_ptr(), self.step_dev.data_ptr(), self.b1, self.b2,

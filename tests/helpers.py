@@ -358,3 +358,21 @@ def rel_err(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     scale = np.maximum(np.abs(b).max(axis=-1, keepdims=True), 1e-30)
     return np.abs(a - b).max(axis=-1, keepdims=True) / scale
+
+
+def trajectory_error(st, ref):
+    """Posterior state after a few Adam iterations against the oracle's: per-element error relative to the largest
+    magnitude of its state row -> dict(q50, q90, q99, max, frac_above_1e4).
+
+    Why quantiles and not a plain bound: the first Adam step is lr*sign(g) and the next ones lr*m/sqrt(v), i.e. the
+    optimiser divides by the gradient's own magnitude.  A voxel whose gradient for one variable nearly cancels (sum over
+    samples and time points) turns a float32-level absolute gradient error into an O(lr) difference of that variable.
+    Any two float32 evaluations of the same graph (the reference's TensorFlow on two devices included) part ways on
+    such isolated voxels; what is checked is that the bulk agrees to the gradient tolerance and the stragglers stay
+    inside the 2*lr-per-iteration envelope."""
+    st, ref = np.asarray(st, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    scale = np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1e-30)
+    err = np.abs(st - ref) / scale
+    q = np.quantile(err, [0.5, 0.9, 0.99])
+    return {"q50": float(q[0]), "q90": float(q[1]), "q99": float(q[2]), "max": float(err.max()),
+            "max_abs": float(np.abs(st - ref).max()), "frac_above_1e-4": float((err > 1e-4).mean())}

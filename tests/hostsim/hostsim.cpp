@@ -171,13 +171,9 @@ extern "C" void hostsim_fill_eps(float *eps, int64_t n_vox, int64_t ld, int64_t 
                                  uint64_t seed, int64_t step) {
     const uint32_t key = rng_key(seed, step);
     for (int64_t w = 0; w < n_vox; ++w)
-        for (int s = 0; s < n_samples; ++s)
-            for (int k = 0; 2 * k < n_par; ++k) {
-                float n0, n1;
-                normal2(key, vox_offset + w, s, k, n0, n1);
-                eps[((int64_t)(2 * k) * n_samples + s) * ld + w] = n0;
-                if (2 * k + 1 < n_par) eps[((int64_t)(2 * k + 1) * n_samples + s) * ld + w] = n1;
-            }
+        for (int j = 0; j < n_par; ++j)
+            for (int s = 0; s < n_samples; ++s)
+                eps[((int64_t)j * n_samples + s) * ld + w] = normal_at(key, vox_offset + w, j, s, n_samples);
 }
 
 // Q(a, x_k), dQ/da, dQ/dx along a sequence of arguments through the running evaluator (model_disp.h:

