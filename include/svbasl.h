@@ -251,8 +251,15 @@ int svbasl_step_spatial(const svbasl_model *model, const svbasl_engine *engine, 
 
 /* Pre-pass of a step with spatial priors: out [n spatial params][S][ld] = theta_{p,s} = mu_p + (L eps_s)_p for
  * every local voxel in [0, n_local) (owned + halo), from engine->state and the step's draws (engine->eps or the
- * Philox stream of `step`).  Neighbours then read each other's samples instead of rebuilding them. */
+ * Philox stream of `step`; with engine->step_dev the iteration is *step_dev + step).  Neighbours then read each
+ * other's samples instead of rebuilding them. */
 int svbasl_sample_spatial(const svbasl_engine *engine, int64_t n_local, int64_t step, float *out, void *stream);
+
+/* The same for the NEXT iteration, right behind a step: the owned voxels [w_begin, w_begin + n_vox) only, from the
+ * state the step has just written, for iteration (*engine->step_dev or 0) + step; a shard-boundary voxel's samples
+ * are also stored into the adjacent ranks' halo columns (engine->peer_lo / peer_hi name THEIR `out` buffers), so the
+ * halo voxels never need a pre-pass or an exchange launch.  Boundary voxels are processed by the first CTAs. */
+int svbasl_sample_spatial_next(const svbasl_engine *engine, int64_t step, float *out, void *stream);
 
 /* Adam update of the global spatial-precision hyper-parameters from ak_grad (after any allreduce). */
 int svbasl_hyper_step(float *log_ak, float *m, float *v, const double *ak_grad, int32_t n, float grad_scale,

@@ -101,6 +101,7 @@ _EXPORTS = {
     "svbasl_step_spatial": (C.c_int, [C.POINTER(Model), C.POINTER(Engine), C.POINTER(Adam), C.POINTER(Hyper), C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
     "svbasl_sample_spatial": (C.c_int, [C.POINTER(Engine), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "svbasl_sample_spatial_next": (C.c_int, [C.POINTER(Engine), C.c_int64, C.c_void_p, C.c_void_p]),
     "svbasl_hyper_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
                                     C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "svbasl_hyper_step_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p,

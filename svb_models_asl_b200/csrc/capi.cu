@@ -335,10 +335,10 @@ static int run_step(const svbasl_model *model, const svbasl_engine *engine, cons
     }
     if (engine->peer_lo || engine->peer_hi) {
         const int64_t nlo = engine->peer_lo ? engine->peer_lo_count : 0, nhi = engine->peer_hi ? engine->peer_hi_count : 0;
-        if (!engine->spatial_samples_out || nlo < 0 || nhi < 0 || nlo + nhi > engine->n_vox ||
+        if (nlo < 0 || nhi < 0 || nlo + nhi > engine->n_vox ||
             (engine->peer_lo && engine->peer_lo_first != engine->w_begin) ||
             (engine->peer_hi && engine->peer_hi_first != engine->w_begin + engine->n_vox - nhi)) {
-            set_error("peer_lo / peer_hi need spatial_samples_out and must name the first / last owned voxels of the launch");
+            set_error("peer_lo / peer_hi must name the first / last owned voxels of the launch");
             return SVBASL_E_INVALID;
         }
     }
@@ -380,21 +380,46 @@ int svbasl_step_spatial(const svbasl_model *model, const svbasl_engine *engine, 
     return run_step(model, engine, adam, 0, nullptr, nullptr, cost_sum, nan_count, stream, hyper);
 }
 
+static int launch_spatial_samples(const svbasl_engine *engine, int64_t first, int64_t count, int64_t step, float *out,
+                                  bool mirror, void *stream) {
+    if (count == 0 || mrf_mask(engine) == 0) return 0;
+    SpatialArgs a;
+    a.e = *engine;
+    if (!mirror) a.e.peer_lo = a.e.peer_hi = nullptr;
+    a.ec = make_engine_const(*engine);
+    a.first = first;
+    a.count = count;
+    a.step = step;
+    a.out = out;
+    spatial_sample_kernel<<<(unsigned)((count + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("spatial_sample_kernel");
+}
+
 int svbasl_sample_spatial(const svbasl_engine *engine, int64_t n_local, int64_t step, float *out, void *stream) {
     if (!engine || !out || !engine->state || n_local < 0 || n_local > engine->ld || engine->n_par < 1 ||
         engine->n_par > SVBASL_MAX_PAR || engine->n_samples < 1) {
         set_error("bad sample_spatial arguments");
         return SVBASL_E_INVALID;
     }
-    if (n_local == 0 || mrf_mask(engine) == 0) return 0;
-    SpatialArgs a;
-    a.e = *engine;
-    a.ec = make_engine_const(*engine);
-    a.n_local = n_local;
-    a.step = step;
-    a.out = out;
-    spatial_sample_kernel<<<(unsigned)((n_local + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(a);
-    return check_launch("spatial_sample_kernel");
+    return launch_spatial_samples(engine, 0, n_local, step, out, false, stream);
+}
+
+int svbasl_sample_spatial_next(const svbasl_engine *engine, int64_t step, float *out, void *stream) {
+    if (!engine || !out || !engine->state || engine->n_vox < 0 || engine->w_begin < 0 ||
+        engine->w_begin + engine->n_vox > engine->ld || engine->n_par < 1 || engine->n_par > SVBASL_MAX_PAR ||
+        engine->n_samples < 1 || engine->eps) {
+        set_error("bad sample_spatial_next arguments (needs the in-kernel draws)");
+        return SVBASL_E_INVALID;
+    }
+    if (engine->peer_lo || engine->peer_hi) {
+        const int64_t nlo = engine->peer_lo ? engine->peer_lo_count : 0, nhi = engine->peer_hi ? engine->peer_hi_count : 0;
+        if (nlo < 0 || nhi < 0 || nlo + nhi > engine->n_vox || (engine->peer_lo && engine->peer_lo_first != engine->w_begin) ||
+            (engine->peer_hi && engine->peer_hi_first != engine->w_begin + engine->n_vox - nhi)) {
+            set_error("peer_lo / peer_hi must name the first / last owned voxels");
+            return SVBASL_E_INVALID;
+        }
+    }
+    return launch_spatial_samples(engine, engine->w_begin, engine->n_vox, step, out, true, stream);
 }
 
 int svbasl_hyper_step(float *log_ak, float *m, float *v, const double *ak_grad, int32_t n, float grad_scale, float lr_t,

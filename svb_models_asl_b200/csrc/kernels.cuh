@@ -296,21 +296,41 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
     }
 }
 
-// Pre-pass for spatial priors: theta samples of every spatially-regularised parameter, all local voxels
+// Pre-pass for spatial priors: theta samples of every spatially-regularised parameter for the voxels
+// [first, first + count) of the local arrays (all local voxels incl. the halo when priming, the owned voxels when it
+// runs right behind a step to prepare the next iteration).  A shard-boundary voxel's samples are ALSO stored into the
+// adjacent rank's halo columns through NVLink peer memory (svbasl_engine.peer_*): the halo "exchange" is these
+// stores.  Boundary voxels are served by the first CTAs so the stores are under way early.
 struct SpatialArgs {
     svbasl_engine e;
     EngineConst ec;
-    int64_t n_local;
-    int64_t step;
+    int64_t first, count;
+    int64_t step;            // added to *e.step_dev when the iteration counter lives on the device
     float *out;              // [n_spatial][S][ld]
 };
 
 static __global__ void __launch_bounds__(kBlock) spatial_sample_kernel(const __grid_constant__ SpatialArgs a) {
-    const int64_t u = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (u >= a.n_local) return;
-    const uint32_t key = rng_key(a.e.seed, a.e.step_dev ? (int64_t)*a.e.step_dev : a.step);
+    int64_t idx = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (idx >= a.count) return;
+    const bool peers = a.e.peer_lo || a.e.peer_hi;
+    if (peers) {
+        const int64_t nlo = a.e.peer_lo ? a.e.peer_lo_count : 0, nhi = a.e.peer_hi ? a.e.peer_hi_count : 0;
+        if (idx >= nlo) idx = idx < nlo + nhi ? a.count - nhi + (idx - nlo) : idx - nhi;
+    }
+    const int64_t u = a.first + idx;
+    const uint32_t key = rng_key(a.e.seed, (a.e.step_dev ? (int64_t)*a.e.step_dev : 0) + a.step);
     const int S = a.e.n_samples, n = a.e.n_par;
     const int64_t ld = a.e.ld;
+    float *lo = (a.e.peer_lo && u >= a.e.peer_lo_first && u < a.e.peer_lo_first + a.e.peer_lo_count)
+                    ? a.e.peer_lo + (u + a.e.peer_lo_shift) : nullptr;
+    float *hi = (a.e.peer_hi && u >= a.e.peer_hi_first && u < a.e.peer_hi_first + a.e.peer_hi_count)
+                    ? a.e.peer_hi + (u + a.e.peer_hi_shift) : nullptr;
+    auto put = [&](int slot, int s, float th) {
+        const int64_t row = (int64_t)slot * S + s;
+        a.out[row * ld + u] = th;
+        if (lo) lo[row * a.e.peer_lo_ld] = th;
+        if (hi) hi[row * a.e.peer_hi_ld] = th;
+    };
     int p_first = 0;
     if (!a.e.eps) {
         // Parameters 0 and 1 (ftiss, delttiss: the usual spatial ones): one Philox call per row serves two samples;
@@ -326,20 +346,18 @@ static __global__ void __launch_bounds__(kBlock) spatial_sample_kernel(const __g
                 sd1 = fexp(0.5f * st[(int64_t)(n + 1) * ld]);
                 od10 = st[(int64_t)(2 * n + stri(1, 0)) * ld];
             }
-            float *o0 = a.out + (int64_t)(s0 >= 0 ? s0 : 0) * S * ld + u;
-            float *o1 = a.out + (int64_t)(s1 >= 0 ? s1 : 0) * S * ld + u;
             for (int s = 0; s < S; s += 2) {
                 float e0a, e0b, e1a = 0.0f, e1b = 0.0f;
                 normal_pair(key, a.e.vox_offset + u, stream_pair(0, s, S), e0a, e0b);
                 if (s1 >= 0) normal_pair(key, a.e.vox_offset + u, stream_pair(1, s, S), e1a, e1b);
                 const bool two = s + 1 < S;
                 if (s0 >= 0) {
-                    o0[(int64_t)s * ld] = mu0 + sd0 * e0a;
-                    if (two) o0[(int64_t)(s + 1) * ld] = mu0 + sd0 * e0b;
+                    put(s0, s, mu0 + sd0 * e0a);
+                    if (two) put(s0, s + 1, mu0 + sd0 * e0b);
                 }
                 if (s1 >= 0) {
-                    o1[(int64_t)s * ld] = (mu1 + od10 * e0a) + sd1 * e1a;
-                    if (two) o1[(int64_t)(s + 1) * ld] = (mu1 + od10 * e0b) + sd1 * e1b;
+                    put(s1, s, (mu1 + od10 * e0a) + sd1 * e1a);
+                    if (two) put(s1, s + 1, (mu1 + od10 * e0b) + sd1 * e1b);
                 }
             }
         }
@@ -347,9 +365,9 @@ static __global__ void __launch_bounds__(kBlock) spatial_sample_kernel(const __g
     for (int p = p_first; p < n; ++p) {
         const int slot = a.ec.sp_slot[p];
         if (slot < 0) continue;
-        for (int s = 0; s < S; ++s)
-            a.out[((int64_t)slot * S + s) * ld + u] = sample_theta(a.e, key, u, p, s);
+        for (int s = 0; s < S; ++s) put(slot, s, sample_theta(a.e, key, u, p, s));
     }
+    if (lo || hi) __threadfence_system();
 }
 
 // Model.evaluate: one thread per (row, time point) element of the reference's [W,S,B] output

@@ -167,12 +167,12 @@ class FusedSvb:
     All arrays are SoA, voxel-fastest, row stride `ld`.  `state` rows: mean[P'], logvar[P'], off-diagonal
     Cholesky rows, ARD log-phi rows (include/svbasl.h).
 
-    Spatial ("M") priors: the same single launch additionally (a) reads the six neighbours' theta samples of this
-    iteration from `sp_bufs[sp_cur]`, (b) writes every voxel's samples of the NEXT iteration into the other buffer -
-    and, sharded over several GPUs, straight into the adjacent ranks' halo columns over NVLink peer memory - and (c)
-    ends with the all-reduce of d(cost)/d(log ak) over peer-memory mailboxes, the Adam step on log ak and the advance
-    of the device-resident iteration counter (svbasl_step_spatial).  `halo_mode`: "peer" (that), "peer+nccl" (peer
-    stores, NCCL all-reduce + separate hyper-step launch), "nccl" (NCCL send/recv of the halo samples, NCCL all-reduce).
+    Spatial ("M") priors: the step reads the six neighbours' theta samples of this iteration from
+    `sp_bufs[sp_cur]`; the samples of the NEXT iteration go into the other buffer - and, sharded over several GPUs,
+    straight into the adjacent ranks' halo columns over NVLink peer memory - and the iteration ends with the all-reduce
+    of d(cost)/d(log ak), the Adam step on log ak and the advance of the device-resident iteration counter.
+    `halo_mode`: "peer" (peer-memory stores + all-reduce over peer-memory mailboxes), "peer+nccl" (peer stores, NCCL
+    all-reduce), "nccl" (NCCL send/recv of the halo samples, NCCL all-reduce).
     """
 
     def __init__(self, model, data, tpts=None, *, ti=None, zoff=None, n_samples=10, batch_size=None,
@@ -229,10 +229,10 @@ class FusedSvb:
         self.nan_count = z(1, dt=torch.int64)
         self.neighbours = device_array(neighbours, self.dev, torch.int32) if neighbours is not None else None
         self.eps = None
-        # how a spatial iteration is launched (measurement switch, SVBASL_SPATIAL_FLOW): "fused" = one launch, next
-        # samples + hyper tail in the step kernel; "separate_tail" = step kernel + hyper-step launch; "prepass" =
-        # round-1 flow, pre-pass kernel + step kernel + hyper-step launch (single GPU / NCCL modes only)
-        self.spatial_flow = os.environ.get("SVBASL_SPATIAL_FLOW", "fused")
+        # how a spatial iteration is launched (SVBASL_SPATIAL_FLOW; see _launch_spatial_iteration): "prepass" = step
+        # kernel + next iteration's pre-pass kernel + hyper step; "separate_tail" = next samples drawn inside the step
+        # kernel + hyper step; "fused" = everything in one launch
+        self.spatial_flow = os.environ.get("SVBASL_SPATIAL_FLOW", "prepass")
         self.plan = None            # ShardPlan of a spatial prior sharded over several ranks
         self.halo_mode = None
         self.reduce_fn = None       # sums a small tensor over all ranks in place (NCCL / gloo)
@@ -381,33 +381,45 @@ class FusedSvb:
             td.barrier()                   # peer stores of the first iteration must not overtake a neighbour's pre-pass
 
     def _launch_spatial_iteration(self):
-        """The launch(es) of one spatial iteration for the current buffer parity (also what enable_graph captures)."""
-        e = self.engine_desc(for_step=True)
+        """The launches of one spatial iteration for the current buffer parity (also what enable_graph captures).
+
+        Default flow ("prepass"): step kernel -> pre-pass kernel for the NEXT iteration over the owned voxels (its
+        samples of shard-boundary voxels also stored into the adjacent ranks' halo columns over NVLink) -> hyper step
+        (all-reduce of the log-ak gradient over peer-memory mailboxes / NCCL, Adam on log ak, counter advance; the
+        all-reduce is also the barrier that makes the mirrored samples visible).  The lightweight pre-pass kernel draws
+        the samples at full occupancy for 17 us per million voxels; drawing them inside the step kernel ("fused",
+        "separate_tail") costs 32 us and the per-CTA completion protocol of the fused tail another 11
+        (profiles/r2_notes.md), so those flows are kept as measured alternatives only."""
         ad = self.adam_desc(1)
         mode = self.halo_mode if (self.plan is not None and self.plan.world > 1) else None
-        fused_tail = mode in (None, "peer") and self.spatial_flow == "fused"
-        if self.spatial_flow == "prepass" and mode in (None, "nccl"):
-            e.spatial_samples_out = None                        # samples of THIS iteration by the pre-pass kernel
-            if mode == "nccl":
-                self.plan.exchange_halo(self.state)
-            L.check(self.lib.svbasl_sample_spatial(C.byref(e), self.ld, 0, self.sp_bufs[self.sp_cur].data_ptr(), _stream_ptr()))
-        hy = self.hyper_desc() if fused_tail else None
+        flow = self.spatial_flow
+        e = self.engine_desc(for_step=True)
+        nxt = self.sp_bufs[1 - self.sp_cur]
+        hy = None
+        if flow == "prepass":
+            es = self.engine_desc(for_step=True)               # descriptor of the sampler: keeps the peer pointers
+            e.spatial_samples_out = None
+            e.peer_lo = e.peer_hi = None
+        elif flow == "fused" and mode in (None, "peer"):
+            hy = self.hyper_desc()
+        elif mode == "nccl":
+            e.peer_lo = e.peer_hi = None
         L.check(self.lib.svbasl_step_spatial(C.byref(self.mdesc), C.byref(e), C.byref(ad),
                                              C.byref(hy) if hy is not None else None, self.cost_hist.data_ptr(),
                                              self.nan_count.data_ptr(), _stream_ptr()))
-        if fused_tail:
+        if hy is not None:
             return
-        if mode == "peer":                                     # separate_tail: the mailbox all-reduce as its own launch
-            hy = self.hyper_desc()
+        if flow == "prepass":
+            L.check(self.lib.svbasl_sample_spatial_next(C.byref(es), 1, nxt.data_ptr(), _stream_ptr()))
+        if mode == "nccl":
+            self.plan.exchange_halo(nxt.view(-1, self.ld))     # ncclSend/Recv of the boundary voxels' next samples
+        if mode == "peer":                                     # mailbox all-reduce + barrier + log-ak step
             L.check(self.lib.svbasl_hyper_step_peers(
                 self.log_ak.data_ptr(), self.ak_m.data_ptr(), self.ak_v.data_ptr(), self.ak_grad.data_ptr(),
                 len(self.mrf), 1.0 / self.n_vox_global, self.lr_t.data_ptr(), self.step_dev.data_ptr(), self.b1, self.b2,
                 self.adam_eps, self.plan.rank, self.plan.world, (C.c_void_p * self.plan.world)(*self._mail_ptrs),
                 self.peer_status.data_ptr(), _stream_ptr()))
             return
-        if mode == "nccl" and self.spatial_flow != "prepass":
-            nxt = self.sp_bufs[1 - self.sp_cur]
-            self.plan.exchange_halo(nxt.view(-1, self.ld))     # ncclSend/Recv of the boundary voxels' next samples
         if mode is not None:
             self.reduce_fn(self.ak_grad)                       # NCCL all-reduce (also orders the peer stores)
         L.check(self.lib.svbasl_hyper_step_dev(self.log_ak.data_ptr(), self.ak_m.data_ptr(), self.ak_v.data_ptr(),
@@ -630,6 +642,8 @@ class HostFeeder:
         f = self.f
         hy = None
         if f.mrf:
+            # host-fed spatial iterations use the single-launch form (next samples and hyper tail inside the step
+            # kernel): svbasl_step_host is one launch per call
             if not f.sp_valid:
                 f._prime_samples()
             torch.cuda.current_stream().synchronize() if self.calls == 0 else None

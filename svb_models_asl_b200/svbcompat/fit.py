@@ -83,17 +83,30 @@ class SvbFit(LogBase):
             n_vox_global=self.data_model.n_nodes, vox_offset=lo, halo=halo, neighbours=neighbours,
             ak_init=float(kwargs.get("ak", 1e-5)), ard_phi_max=kwargs.get("ard_phi_max", 1e6),
             latent_weight=float(kwargs.get("latent_weight", 1.0)), max_steps=epochs * n_batches + 1)
-        # initial posterior (svb: post_init(param, t, data) -> (mean, var) in MODEL space, mapped to internal).
-        # Each rank initialises its own shard; the per-voxel reductions of the data (mean / max / variance / time of
-        # the maximum over time, aslrest.py:467,490,497-501) come from the device (svbasl_init_stats) and travel
-        # with the `data` argument (ops.InitData), so nothing of size [W, T] is reduced on the host.
         own = slice(halo[0], halo[0] + (hi - lo))
         stats = None
         if kwargs.get("device_init", True):
             stats = {k: v[own].cpu().numpy() for k, v in self.fused.init_stats().items()}
         local_data = InitData(data[lo:hi], stats)
         local_data.voxel_slice = slice(lo, hi)
-        local_t = tpts[lo:hi]
+        means, variances = self._initial_posterior(tpts[lo:hi], local_data)
+        self.fused.set_posterior(means, variances)
+        if "M" in prior_types:
+            # "peer": next-iteration samples of boundary voxels stored straight into the neighbours' halos over NVLink
+            # peer memory, log-ak all-reduce over peer-memory mailboxes (the iteration is replayed as a CUDA graph);
+            # "peer+nccl": the all-reduce by NCCL; "nccl": send/recv of the halo samples
+            mode = kwargs.get("halo_mode", "peer")
+            if self.world > 1:
+                self.fused.shard(plan, halo_mode=mode, reduce_fn=ShardPlan.allreduce_sum)
+            if kwargs.get("use_graph", True) and (self.world == 1 or mode in ("peer", "peer+nccl")):
+                self.fused.enable_graph()
+
+    def _initial_posterior(self, local_t, local_data):
+        """svb: post_init(param, t, data) -> (mean, var) in MODEL space, mapped to internal values.  Each rank
+        initialises its own shard; the per-voxel reductions of the data (mean / max / variance / time of the maximum
+        over time, aslrest.py:467,490,497-501) come from the device (svbasl_init_stats) and travel with the `data`
+        argument (ops.InitData), so nothing of size [W, T] is reduced on the host."""
+        n = len(local_data)
         means, variances = [], []
         for p in self.params:
             mean, var = None, None
@@ -102,21 +115,46 @@ class SvbFit(LogBase):
                 if mean is not None:
                     mean = p.post_dist.transform.int_values(np.asarray(mean, dtype=np.float32))
             if mean is None:
-                mean = np.full(hi - lo, np.mean(p.post_dist.mean), dtype=np.float32)
+                mean = np.full(n, np.mean(p.post_dist.mean), dtype=np.float32)
             if var is None:
-                var = np.full(hi - lo, np.mean(p.post_dist.var), dtype=np.float32)
-            means.append(np.broadcast_to(np.asarray(mean, dtype=np.float32), (hi - lo,)))
-            variances.append(np.broadcast_to(np.asarray(var, dtype=np.float32), (hi - lo,)))
-        self.fused.set_posterior(means, variances)
-        if "M" in prior_types:
-            # "peer": next-iteration samples of boundary voxels stored straight into the neighbours' halos and the
-            # log-ak all-reduce over peer-memory mailboxes, both inside the step kernel (one launch per iteration,
-            # replayed as a CUDA graph); "peer+nccl": the all-reduce by NCCL; "nccl": send/recv of the halo samples
+                var = np.full(n, np.mean(p.post_dist.var), dtype=np.float32)
+            means.append(np.broadcast_to(np.asarray(mean, dtype=np.float32), (n,)))
+            variances.append(np.broadcast_to(np.asarray(var, dtype=np.float32), (n,)))
+        return means, variances
+
+    def setup_from_device(self, data_dev, plan, ti, zoff_dev, batch_size, sample_size, learning_rate, max_steps,
+                          **kwargs):
+        """The same set-up as train() performs, for data that already live on this rank's GPU: `data_dev` [T, ld]
+        covers the rank's local voxel range of `plan` (halo included), time points in the model's low-rank form
+        (`ti` [T] + `zoff_dev` [ld], aslrest.py:438-440).  Used for volumes too large to stage through host arrays
+        (bench.py's 10 M-voxel spatial fit); everything downstream (FusedSvb, posterior initialisers, sharding) is
+        the code path of _setup()."""
+        self.plan = plan
+        self.lo, self.hi = plan.lo, plan.hi
+        prior_types = [p.prior_type for p in self.params]
+        spatial = "M" in prior_types
+        halo = (plan.halo_lo, plan.halo_hi) if spatial else (0, 0)
+        self.fused = FusedSvb(
+            self.model, data_dev, None, ti=ti, zoff=zoff_dev, n_samples=sample_size, batch_size=batch_size,
+            latent="numeric", cov_llt=(kwargs.get("cov_convention", "LtL") == "LLt"), learning_rate=learning_rate,
+            seed=int(kwargs.get("seed", 1)), prior_types=prior_types,
+            prior_means=[np.mean(p.prior_dist.mean) for p in self.params],
+            prior_vars=[np.mean(p.prior_dist.var) for p in self.params], n_vox_global=plan.n_global, vox_offset=plan.lo,
+            halo=halo, neighbours=plan.neighbours_local if spatial else None, ak_init=float(kwargs.get("ak", 1e-5)),
+            ard_phi_max=kwargs.get("ard_phi_max", 1e6), latent_weight=float(kwargs.get("latent_weight", 1.0)),
+            max_steps=max_steps)
+        own = slice(halo[0], halo[0] + plan.n_own)
+        stats = {k: v[own].cpu().numpy() for k, v in self.fused.init_stats().items()}
+        local = InitData(np.empty((plan.n_own, 0), dtype=np.float32), stats)
+        local.voxel_slice = slice(plan.lo, plan.hi)
+        self.fused.set_posterior(*self._initial_posterior(None, local))
+        if spatial:
             mode = kwargs.get("halo_mode", "peer")
-            if self.world > 1:
+            if plan.world > 1:
                 self.fused.shard(plan, halo_mode=mode, reduce_fn=ShardPlan.allreduce_sum)
-            if kwargs.get("use_graph", True) and (self.world == 1 or mode in ("peer", "peer+nccl")):
+            if kwargs.get("use_graph", True) and (plan.world == 1 or mode in ("peer", "peer+nccl")):
                 self.fused.enable_graph()
+        return self.fused
 
     # ------------------------------------------------------------------
     def train(self, tpts, data, batch_size=None, epochs=100, learning_rate=0.1, sample_size=None, display_step=1,

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "1", "--cpu-voxels", "500"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--warmup", "1", "--voxels", "500"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, res.stdout
@@ -25,12 +25,14 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    # the reference arm runs the configuration it is asked for (the driver asks for none: the GPU arm's 1M voxels)
+    assert d["config"]["voxels_per_gpu"] == 500 and d["config"]["name"] == "sim_art"
 
 
 def test_reference_arm_is_silent_on_other_ranks():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
-                          "--steps", "1", "--warmup", "1", "--cpu-voxels", "500"], capture_output=True, text=True,
+                          "--steps", "1", "--warmup", "1", "--voxels", "500"], capture_output=True, text=True,
                          timeout=600, cwd=ROOT, env=env)
     assert res.returncode == 0 and res.stdout.strip() == ""
 

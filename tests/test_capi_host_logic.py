@@ -171,6 +171,7 @@ def test_null_and_range_checks_of_the_small_entry_points(lib):
     assert lib.svbasl_mailbox_bytes(8) == 2 * 8 * 40 and lib.svbasl_mailbox_bytes(0) == 0
     assert lib.svbasl_shared_alloc(0, None, None) < 0
     assert lib.svbasl_sample_spatial(None, 0, 0, None, None) < 0
+    assert lib.svbasl_sample_spatial_next(None, 0, None, None) < 0
     assert lib.svbasl_abi_version() == 2
 
 
