@@ -7,7 +7,16 @@ MODELS = {"aslrest": AslRestModel, "aslrest_disp": AslRestDisp, "aslnn": AslNNMo
 
 
 def get_model_class(name):
-    """What svb does through the `svb.models` entry-point group (setup.py:89-95)."""
-    if name not in MODELS:
-        raise ValueError("No such model: %s (known: %s)" % (name, ", ".join(sorted(MODELS))))
-    return MODELS[name]
+    """What svb does through the `svb.models` entry-point group (setup.py:89-95): installed distributions that
+    register models under that group are found by name (pyproject.toml registers these three the same way); the
+    built-in table answers first, so an uninstalled checkout works too."""
+    if name in MODELS:
+        return MODELS[name]
+    try:
+        from importlib.metadata import entry_points
+        for ep in entry_points(group="svb.models"):
+            if ep.name == name:
+                return ep.load()
+    except Exception:  # noqa: BLE001 - discovery is best effort; the error below names what is known
+        pass
+    raise ValueError("No such model: %s (known: %s)" % (name, ", ".join(sorted(MODELS))))

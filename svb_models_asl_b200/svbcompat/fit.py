@@ -158,9 +158,13 @@ class SvbFit(LogBase):
 
     # ------------------------------------------------------------------
     def train(self, tpts, data, batch_size=None, epochs=100, learning_rate=0.1, sample_size=None, display_step=1,
-              iters_per_launch=1, **kwargs):
+              iters_per_launch=None, **kwargs):
         """Returns the training history dict (mean_cost per epoch; voxel cost / parameter histories when the
-        corresponding save_* option is set)."""
+        corresponding save_* option is set).
+
+        iters_per_launch: iterations fused into one kernel launch (voxel-wise priors; svbasl_adam.n_iters).  Default:
+        8, lowered to the number of batches per epoch when a per-epoch history is recorded (save_cost_history /
+        save_param_history need the state at every epoch boundary)."""
         sample_size = sample_size or 5
         self._setup(tpts, data, batch_size, sample_size, learning_rate, epochs, **kwargs)
         f = self.fused
@@ -172,6 +176,7 @@ class SvbFit(LogBase):
         vc = torch.zeros(epochs + 1, f.n_vox, device=f.dev) if want_vc else None
         ph = torch.zeros(epochs + 1, f.N, f.n_vox, device=f.dev) if want_ph else None
         sl = slice(f.halo[0], f.halo[0] + f.n_vox)
+        stream = kwargs.get("log_stream") if self.rank == 0 else None
 
         def record(epoch):
             if want_vc or epoch == 0:
@@ -182,34 +187,49 @@ class SvbFit(LogBase):
             if want_ph:
                 ph[epoch] = f.state[:f.N, sl]
 
+        def log(epoch):
+            if stream and display_step and epoch % max(1, display_step) == 0:
+                # one host sync per displayed epoch; keep display_step large for big fits
+                mc = float(f.cost_hist[(epoch - 1) * n_batches:epoch * n_batches].mean()) / f.n_vox
+                stream.write(" - Epoch %04d: mean cost=%f (shard of %i voxels)\n" % (epoch, mc, f.n_vox))
+
         record(0)
         t0 = time.time()
-        fuse = max(1, int(iters_per_launch)) if not f.mrf else 1
-        for epoch in range(epochs):
-            done = 0
-            acc = torch.zeros((), device=f.dev, dtype=torch.float64)
-            while done < n_batches:
-                k = min(fuse, n_batches - done)
-                acc = acc + f.step(k).sum()
-                done += k
-            if f.mrf and self.world > 1 and (epoch + 1) % 64 == 0:
-                f.check_peers()                                 # a lost rank surfaces here, not at teardown
-            if not want_vc:
-                cost_dev[epoch + 1] = acc / n_batches          # mean of the batch costs (no extra launch)
-            record(epoch + 1)
-            if display_step and self.rank == 0 and (epoch + 1) % max(1, display_step) == 0 and kwargs.get("log_stream"):
-                # one host sync per displayed epoch; keep display_step large for big fits
-                mc = float(cost_dev[epoch + 1]) / f.n_vox
-                kwargs["log_stream"].write(" - Epoch %04d: mean cost=%f (shard of %i voxels)\n" % (epoch + 1, mc, f.n_vox))
+        total = epochs * n_batches
+        per_epoch = want_vc or want_ph
+        fuse = 1 if f.mrf else max(1, min(int(iters_per_launch or 8), f.max_fuse))
+        done = 0
+        while done < total:
+            # a launch never crosses an epoch boundary at which something is recorded or displayed
+            if per_epoch:
+                stop = (done // n_batches + 1) * n_batches
+            elif stream and display_step:
+                span = n_batches * max(1, display_step)
+                stop = min(total, (done // span + 1) * span)
+            else:
+                stop = total
+            k = min(fuse, stop - done)
+            f.step(k)
+            done += k
+            if done % n_batches == 0:
+                epoch = done // n_batches
+                if per_epoch:
+                    record(epoch)
+                log(epoch)
+                if f.mrf and self.world > 1 and epoch % 64 == 0:
+                    f.check_peers()                             # a lost rank surfaces here, not at teardown
         if f.mrf:
             f.check_peers()
+        if not want_vc:
+            # mean of each epoch's batch costs, from the per-iteration sums the kernels left on the device
+            cost_dev[1:] = f.cost_hist[:total].view(epochs, n_batches).mean(dim=1)
         torch.cuda.synchronize()
         self.runtime = time.time() - t0
-        total = cost_dev.clone()
+        total_cost = cost_dev.clone()
         if self.world > 1:
             import torch.distributed as td
-            td.all_reduce(total)                                # the only collective: scalar cost, for reporting
-        hist["mean_cost"] = (total / self.data_model.n_nodes).cpu().numpy()
+            td.all_reduce(total_cost)                           # the only collective: scalar cost, for reporting
+        hist["mean_cost"] = (total_cost / self.data_model.n_nodes).cpu().numpy()
         if want_vc:
             hist["voxel_cost"] = vc.T.cpu().numpy()
         if want_ph:
