@@ -156,6 +156,109 @@ struct VoxelStep {
         }
     }
 
+    // Per-voxel prior / posterior terms that the sample loop and the closing algebra share
+    struct Terms {
+        float sd[N];                                   // exp(logvar / 2)
+        float pm[N], pinv[N], plog[N], phi_live[N];    // prior mean, 1/variance, log variance; ARD gradient gate
+        float lw_pinv[N];                              // latent_weight / prior variance
+    };
+
+    SVB_HD void prior_terms(const svbasl_engine &e, const EngineConst &ec, Terms &t) const {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            t.sd[i] = fexp(0.5f * lv[i]);
+            t.pm[i] = e.prior_mean[i];
+            if (e.prior_type[i] == SVBASL_PRIOR_ARD) {
+                float phi = fexp(lphi[i]);
+                bool clipped = (e.ard_phi_max > 0.0f) && (phi > e.ard_phi_max);
+                phi = clipped ? e.ard_phi_max : phi;
+                t.pinv[i] = phi;
+                t.plog[i] = -flog(phi);
+                t.phi_live[i] = clipped ? 0.0f : 1.0f;
+            } else {
+                t.pinv[i] = ec.pinv[i];
+                t.plog[i] = ec.plog[i];
+                t.phi_live[i] = 0.0f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) t.lw_pinv[i] = e.latent_weight * t.pinv[i];
+    }
+
+    // Closing algebra of elbo_grad: from the sums over samples (a_mu = sum_s g_s, a_L = sum_s g_s eps_s^T,
+    // a_hyp = sum_s lw (theta - m)^2 / v or the MRF log-ak share, cost = sum_s of the per-sample cost) to the cost of
+    // the voxel and the gradients g_* (latent-loss constants, 1/S, entropy or closed-form KL, chain rule to logvar).
+    SVB_HD float finish(const svbasl_engine &e, const EngineConst &ec, const Terms &t, float *a_mu, float *a_L, float *a_hyp,
+                        float cost, bool numeric) {
+        const int S = e.n_samples;
+        const float lw = e.latent_weight;
+        const float invS = ec.inv_s;
+        const float *sd = t.sd, *pm = t.pm, *pinv = t.pinv, *plog = t.plog, *phi_live = t.phi_live;
+        if (numeric) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                if (!SPATIAL || e.prior_type[i] != SVBASL_PRIOR_MRF) {
+                    const float q = a_hyp[i];                           // sum_s lw (theta-m)^2 / v
+                    cost += 0.5f * q + (float)S * lw * 0.5f * plog[i];
+                    a_hyp[i] = 0.5f * (q - (float)S * lw);              // sum_s lw/2 ((theta-m)^2/v - 1)
+                }
+            }
+        }
+        cost *= invS;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { a_mu[i] *= invS; a_hyp[i] *= invS; }
+#pragma unroll
+        for (int k = 0; k < NT; ++k) a_L[k] *= invS;
+
+        if (numeric) {
+            // entropy term -1/2 log det(cov) = -sum_i log L_ii
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                cost -= lw * 0.5f * lv[i];
+                a_L[tri(i, i)] -= lw * frcp(sd[i]);
+            }
+        } else {
+            // closed-form KL( N(mu, cov) || N(pm, diag(pv)) ), cov = L^T L (svb) or L L^T
+            float kl = 0.0f;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const float dm = mu[i] - pm[i];
+                float cii = 0.0f;     // cov_ii
+                if (e.cov_llt) {
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) {
+                        const float l = (j == i) ? sd[i] : od[stri(i, j)];
+                        cii += l * l;
+                        a_L[tri(i, j)] += lw * l * pinv[i];
+                    }
+                } else {
+#pragma unroll
+                    for (int r = i; r < N; ++r) {
+                        const float l = (r == i) ? sd[i] : od[stri(r, i)];
+                        cii += l * l;
+                        a_L[tri(r, i)] += lw * l * pinv[i];
+                    }
+                }
+                kl += cii * pinv[i] + dm * dm * pinv[i] - 1.0f + plog[i] - lv[i];
+                a_mu[i] += lw * dm * pinv[i];
+                a_L[tri(i, i)] -= lw * frcp(sd[i]);
+                a_hyp[i] = lw * 0.5f * (pinv[i] * (cii + dm * dm) - 1.0f);
+            }
+            cost += lw * 0.5f * kl;
+        }
+        const float gs = e.grad_scale;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            g_mu[i] = gs * a_mu[i];
+            g_lv[i] = gs * a_L[tri(i, i)] * 0.5f * sd[i];
+            g_lphi[i] = gs * a_hyp[i] * phi_live[i];
+            ak_out[i] = a_hyp[i];
+#pragma unroll
+            for (int j = 0; j < i; ++j) g_od[stri(i, j)] = gs * a_L[tri(i, j)];
+        }
+        return cost;
+    }
+
     // Cost of this voxel for one batch, gradients left in g_*.  Returns the un-scaled cost.
     SVB_HD float elbo_grad(const DevModel &md, const svbasl_engine &e, const EngineConst &ec, int64_t w, int64_t step,
                            int row0, const NbTile nbt = NbTile{nullptr, 0, -1, 0u}) {
@@ -171,28 +274,9 @@ struct VoxelStep {
         acc.load(e, w, row0);
         M::bind_times(md, vox, acc);
 
-        float sd[N];
-        float pm[N], pinv[N], plog[N], phi_live[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            sd[i] = fexp(0.5f * lv[i]);
-            pm[i] = e.prior_mean[i];
-            if (e.prior_type[i] == SVBASL_PRIOR_ARD) {
-                float phi = fexp(lphi[i]);
-                bool clipped = (e.ard_phi_max > 0.0f) && (phi > e.ard_phi_max);
-                phi = clipped ? e.ard_phi_max : phi;
-                pinv[i] = phi;
-                plog[i] = -flog(phi);
-                phi_live[i] = clipped ? 0.0f : 1.0f;
-            } else {
-                pinv[i] = ec.pinv[i];
-                plog[i] = ec.plog[i];
-                phi_live[i] = 0.0f;
-            }
-        }
-        float lw_pinv[N];                              // latent_weight / prior variance
-#pragma unroll
-        for (int i = 0; i < N; ++i) lw_pinv[i] = lw * pinv[i];
+        Terms tm;
+        prior_terms(e, ec, tm);
+        const float *sd = tm.sd, *pm = tm.pm, *lw_pinv = tm.lw_pinv;
         // a_hyp[i]: ARD log-phi gradient (ARD parameters) or log-ak gradient share (spatial parameters)
         float a_mu[N], a_L[NT], a_hyp[N];
 #pragma unroll
@@ -292,70 +376,7 @@ struct VoxelStep {
                 for (int j = 0; j <= i; ++j) a_L[tri(i, j)] += g[i] * eps[j];
             }
         }
-        const float invS = ec.inv_s;
-        if (numeric) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                if (!SPATIAL || e.prior_type[i] != SVBASL_PRIOR_MRF) {
-                    const float q = a_hyp[i];                           // sum_s lw (theta-m)^2 / v
-                    cost += 0.5f * q + (float)S * lw * 0.5f * plog[i];
-                    a_hyp[i] = 0.5f * (q - (float)S * lw);              // sum_s lw/2 ((theta-m)^2/v - 1)
-                }
-            }
-        }
-        cost *= invS;
-#pragma unroll
-        for (int i = 0; i < N; ++i) { a_mu[i] *= invS; a_hyp[i] *= invS; }
-#pragma unroll
-        for (int k = 0; k < NT; ++k) a_L[k] *= invS;
-
-        if (numeric) {
-            // entropy term -1/2 log det(cov) = -sum_i log L_ii
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                cost -= lw * 0.5f * lv[i];
-                a_L[tri(i, i)] -= lw * frcp(sd[i]);
-            }
-        } else {
-            // closed-form KL( N(mu, cov) || N(pm, diag(pv)) ), cov = L^T L (svb) or L L^T
-            float kl = 0.0f;
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const float dm = mu[i] - pm[i];
-                float cii = 0.0f;     // cov_ii
-                if (e.cov_llt) {
-#pragma unroll
-                    for (int j = 0; j <= i; ++j) {
-                        const float l = (j == i) ? sd[i] : od[stri(i, j)];
-                        cii += l * l;
-                        a_L[tri(i, j)] += lw * l * pinv[i];
-                    }
-                } else {
-#pragma unroll
-                    for (int r = i; r < N; ++r) {
-                        const float l = (r == i) ? sd[i] : od[stri(r, i)];
-                        cii += l * l;
-                        a_L[tri(r, i)] += lw * l * pinv[i];
-                    }
-                }
-                kl += cii * pinv[i] + dm * dm * pinv[i] - 1.0f + plog[i] - lv[i];
-                a_mu[i] += lw * dm * pinv[i];
-                a_L[tri(i, i)] -= lw * frcp(sd[i]);
-                a_hyp[i] = lw * 0.5f * (pinv[i] * (cii + dm * dm) - 1.0f);
-            }
-            cost += lw * 0.5f * kl;
-        }
-        const float gs = e.grad_scale;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            g_mu[i] = gs * a_mu[i];
-            g_lv[i] = gs * a_L[tri(i, i)] * 0.5f * sd[i];
-            g_lphi[i] = gs * a_hyp[i] * phi_live[i];
-            ak_out[i] = a_hyp[i];
-#pragma unroll
-            for (int j = 0; j < i; ++j) g_od[stri(i, j)] = gs * a_L[tri(i, j)];
-        }
-        return cost;
+        return finish(e, ec, tm, a_mu, a_L, a_hyp, cost, numeric);
     }
 
     SVB_HD bool grads_finite() const {

@@ -8,6 +8,7 @@ peak |signal| of the case), cost and gradients 1e-4 relative in float32.
 """
 import ctypes as C
 import math
+import os
 import zlib
 
 import numpy as np
@@ -729,3 +730,44 @@ def test_size_independent_properties_at_the_benchmark_size(be):
         parts_g[:, w0:w0 + nv] = g[:, w0:w0 + nv]
     np.testing.assert_array_equal(parts_c, cost)
     np.testing.assert_array_equal(parts_g, grad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["casl_tiss", "casl_tiss_art", "pasl_tiss_art", "casl_fixed_disp", "casl_as_written",
+                                  "casl_noatt"])
+def test_disp_warp_per_voxel_kernel_equals_thread_per_voxel_kernel(case, record_error):
+    """aslrest_disp runs with one warp per voxel on the GPU (csrc/disp_warp.cuh: the (sample, grid point) evaluations
+    of a voxel flattened over the 32 lanes, running incomplete-gamma values and the tissue recurrence as segmented warp
+    scans).  Same call, both kernels (SVBASL_DISP_SCALAR forces the one-thread-per-voxel kernel): cost, gradient and
+    one Adam step agree to float32 rounding, for T = 48 / B = 6 strided batches and in-kernel draws as well."""
+    be = H.Backend("cuda")
+    cfg = _disp_cfg(case)
+    rng = np.random.default_rng(zlib.crc32(case.encode()) + 7)
+    W = 70
+    spec = H.aslrest_spec(cfg, n_samples=10, t_full=48)
+    prob = H.synth_problem(cfg, spec, W, rng, repeats=8, noise_sd=0.5)
+    m = be.model_desc(cfg)
+    out = {}
+    for which in ("warp", "scalar"):
+        if which == "scalar":
+            os.environ["SVBASL_DISP_SCALAR"] = "1"
+        try:
+            e, bufs = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], None, n_batch=6, t_row0=3,
+                                     t_row_stride=8, seed=5)
+            cost, grad, csum = be.elbo_grad(m, e, spec.n_state, step=2)
+            ad, _ab = be.adam_desc(spec.n_state, W, 0.05, 4, step0=2)
+            s_sum, nanc = be.step(m, e, ad)
+            out[which] = (cost, grad, csum, be.get(bufs["state"]), s_sum, nanc)
+        finally:
+            os.environ.pop("SVBASL_DISP_SCALAR", None)
+    cw, gw, sw, stw, ssw, nw = out["warp"]
+    cs, gs, ss, sts, sss, ns = out["scalar"]
+    assert nw == 0 and ns == 0 and np.isfinite(gw).all()
+    live = np.abs(gs).max(axis=1) > 0
+    rows = (np.linalg.norm(gw - gs, axis=1)[live] / np.linalg.norm(gs, axis=1)[live]).max()
+    record_error("disp_warp_vs_scalar/%s" % case, cost_rel=float(np.abs(cw - cs).max() / np.abs(cs).max()),
+                 grad_row_rel=float(rows), state_rel=float(H.rel_err(stw, sts).max()))
+    np.testing.assert_allclose(cw, cs, rtol=2e-5, atol=2e-5 * np.abs(cs).max())
+    assert rows <= 5e-5, rows
+    assert sw == pytest.approx(ss, rel=1e-5) and ssw[0] == pytest.approx(sss[0], rel=1e-5)
+    assert np.abs(sts - prob["state"]).max() > 1e-3 and H.rel_err(stw, sts).max() <= 2e-4
