@@ -33,7 +33,13 @@
 
 namespace svb {
 
-constexpr int kDwWarps = 4;               // voxels (warps) per CTA
+#ifndef SVB_DW_PHASE_BARRIER
+#define SVB_DW_PHASE_BARRIER 1
+#endif
+#ifndef SVB_DW_WARPS
+#define SVB_DW_WARPS 8
+#endif
+constexpr int kDwWarps = SVB_DW_WARPS;    // voxels (warps) per CTA; the warps of a CTA walk the phases together
 constexpr int kDwNtMax = 64;              // convolution grid points supported
 constexpr int kDwBMax = 32;               // time points per batch supported (lane = time point)
 constexpr int kDwSMax = 32;               // samples supported (lane = sample)
@@ -62,6 +68,15 @@ __device__ __forceinline__ void gamma_quad(const GammaConst &g, float from, floa
     dJ = hw * s1;
 }
 
+// rarely taken paths, kept out of line: the kernel's instruction footprint decides how often its warps - each in a
+// different phase - miss the instruction cache (profiles/r2_notes.md)
+static __device__ __noinline__ void igammac_d_slow(const GammaConst &g, float x, float lnx, float &Q, float &dQa, float &dQx) {
+    igammac_d(g, x, lnx, Q, dQa, dQx);
+}
+static __device__ __noinline__ void gamma_series14_slow(const GammaConst &g, float x, float lnx, float &P, float &J) {
+    gamma_series14(g, x, lnx, P, J);
+}
+
 template <int N, int P>
 struct DwRow {                            // per-sample table row (shared memory)
     float x[P > 0 ? P : 1], dx[P > 0 ? P : 1], eps[N];
@@ -74,11 +89,31 @@ template <class M>
 struct DwLayout {
     static constexpr int N = M::P + 1;
     typedef DwRow<N, M::P> Row;
-    // floats per warp: rows, P1/J1/D1 [S][NT], C [4][S][NT], time-point tables
-    static __host__ __device__ size_t floats(int S, int nt) {
-        return (sizeof(Row) * (size_t)S + 3) / 4 + (size_t)7 * S * nt + 4 * kDwBMax + 2 * kDwSMax + 8;
+    // floats per warp: rows, P1/J1/D1 [S][NT], tissue curve at the grid points the time points need [4][S][2B],
+    // time-point tables, item offsets, item map (uint16 per (sample, grid point))
+    static constexpr int NV = 2 * N + N * (N + 1) / 2 + 1;          // partial sums per lane: a_mu, a_hyp, a_L, cost
+    static constexpr int kRowsMax = 80;                              // state rows staged per warp (n_state <= 74)
+    static __host__ __device__ size_t grid_floats(int S, int nt) {   // P1/J1/D1, later the reduction tile [NV][33] + totals
+        const size_t a = (size_t)3 * S * nt, b = (size_t)NV * 33 + NV;
+        return a > b ? a : b;
+    }
+    static __host__ __device__ size_t floats(int S, int nt, int nb) {
+        return (sizeof(Row) * (size_t)S + 3) / 4 + grid_floats(S, nt) + (size_t)8 * S * nb + 4 * kDwBMax + 2 * kDwSMax + 8 +
+               (size_t)S * nt + 4 * kRowsMax;
     }
 };
+
+// End of a phase.  The shared-memory tables are private to a warp, so __syncwarp() is all correctness needs; the CTA-wide
+// barrier keeps the warps of a CTA in the same phase, i.e. in the same stretch of the kernel's ~5,000 instructions: with
+// 16 warps per SM each in a phase of its own the instruction cache missed 29 % of its requests and `no_instruction`
+// was the top stall (profiles/r2_notes.md).
+__device__ __forceinline__ void dw_phase_sync() {
+#if SVB_DW_PHASE_BARRIER
+    __syncthreads();
+#else
+    __syncwarp();
+#endif
+}
 
 __device__ __forceinline__ int warp_incl_scan_int(int v, int lane) {
 #pragma unroll
@@ -97,7 +132,7 @@ __device__ __forceinline__ int dw_find(const int *off, int S, int idx) {
 }
 
 template <class M, int FL>
-__global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(32 * kDwWarps, 16 / kDwWarps) disp_warp_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ float dw_smem[];
     __shared__ float red[kDwWarps];
     typedef VoxelStep<M, 0, FL> VS;
@@ -117,18 +152,31 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
     const int mshift = (int)(tau * inv_h + 0.5f);              // tau / h, an integer (checked by the launcher)
 
     // ---- warp-private shared memory ----
-    float *base = dw_smem + (size_t)wip * DwLayout<M>::floats(S, nt);
+    float *base = dw_smem + (size_t)wip * DwLayout<M>::floats(S, nt, nb);
     Row *rows = reinterpret_cast<Row *>(base);
     float *P1 = base + (sizeof(Row) * (size_t)S + 3) / 4;
-    float *J1 = P1 + (size_t)S * nt, *D1 = J1 + (size_t)S * nt, *CC = D1 + (size_t)S * nt;     // CC [4][S][nt]
-    float *sm_t = CC + (size_t)4 * S * nt, *sm_y = sm_t + kDwBMax, *sm_fr = sm_y + kDwBMax;
+    float *J1 = P1 + (size_t)S * nt, *D1 = J1 + (size_t)S * nt;
+    float *CC = P1 + DwLayout<M>::grid_floats(S, nt);                                          // CC [4][S][2 nb]
+    const int nslot = 2 * nb;
+    float *sm_t = CC + (size_t)4 * S * nslot, *sm_y = sm_t + kDwBMax, *sm_fr = sm_y + kDwBMax;
     int *sm_lo = reinterpret_cast<int *>(sm_fr + kDwBMax);
     int *off_a = sm_lo + kDwBMax, *off_b = off_a + kDwSMax + 1;          // item offsets per sample (two lists)
+    unsigned short *imap = reinterpret_cast<unsigned short *>(off_b + kDwSMax + 1 + 6);      // item -> (s << 6) | k
+    unsigned short *imap_a = imap + (size_t)S * nt;                                           // the same for the x <= 2 list
+    float *st_sm = reinterpret_cast<float *>(imap_a + (size_t)S * nt);                        // staged state / m / v / grad rows
+    float *m_sm = st_sm + DwLayout<M>::kRowsMax, *v_sm = m_sm + DwLayout<M>::kRowsMax, *g_sm = v_sm + DwLayout<M>::kRowsMax;
+    const int n_state = a.n_state;
+    // the voxel's state and Adam moments: one row per lane, all in flight at once (the closing algebra reads them from
+    // shared memory; row by row from global memory it was a chain of 2 x 36 dependent round trips)
+    for (int r = lane; r < n_state; r += 32) {
+        st_sm[r] = e.state[(int64_t)r * e.ld + w];
+        if (update) {
+            m_sm[r] = a.ad.m[(int64_t)r * e.ld + w];
+            v_sm[r] = a.ad.v[(int64_t)r * e.ld + w];
+        }
+    }
+    __syncwarp();
 
-    VS vs;
-    vs.load(e, w);
-    typename VS::Terms tm;
-    vs.prior_terms(e, a.ec, tm);
     const EngineConst &ec = a.ec;
     const int64_t step = e.step_dev ? (int64_t)*e.step_dev : a.step;
     const int row0 = (update && a.ad.n_batches > 1) ? (int)(step % a.ad.n_batches) : e.t_row0;
@@ -139,6 +187,7 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
     // ---- time points of the batch: lane = time point ----
     int last = 0;
     float tmax = 0.0f;
+    unsigned long long need = 0ull;
     {
         const int64_t stride = (int64_t)e.t_row_stride * e.ld;
         float tv = 0.0f, yv = 0.0f;
@@ -157,6 +206,10 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
         }
         last = __reduce_max_sync(FULL, lane < nb ? lo + 1 : 0);
         tmax = __uint_as_float(__reduce_max_sync(FULL, lane < nb ? __float_as_uint(fmax2(tv, 0.0f)) : 0u));
+        // grid points whose tissue-curve value some time point interpolates from: bits lo_b and lo_b + 1
+        const unsigned m0 = lane < nb ? ((lo < 32 ? 1u << lo : 0u) | (lo + 1 < 32 ? 1u << (lo + 1) : 0u)) : 0u;
+        const unsigned m1 = lane < nb ? ((lo >= 32 ? 1u << (lo - 32) : 0u) | (lo + 1 >= 32 ? 1u << (lo + 1 - 32) : 0u)) : 0u;
+        need = (unsigned long long)__reduce_or_sync(FULL, m0) | ((unsigned long long)__reduce_or_sync(FULL, m1) << 32);
     }
 
     // partial sums of this lane: a_mu = sum_s g_s, a_L = sum_s g_s eps_s^T, a_hyp, cost
@@ -167,14 +220,36 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
     for (int k = 0; k < NT; ++k) pa_L[k] = 0.0f;
 
     // ---- phase 0: lane = sample ----
+    // (the posterior state and the prior terms are needed here and in the closing algebra only: they are loaded again
+    // there rather than held in ~80 registers through the grid phases)
     int my_small = 0, my_npts = 0;
+    // draws of all samples: one Philox call = one posterior row of two samples, the N * ceil(S/2) calls spread over the lanes
+    if (!LEAN && e.eps) {
+        for (int idx = lane; idx < N * S; idx += 32) {
+            const int j = idx / S, s = idx - j * S;
+            rows[s].eps[j] = e.eps[((int64_t)j * S + s) * e.ld + w];
+        }
+    } else {
+        const int hp = (S + 1) >> 1;
+        for (int p = lane; p < N * hp; p += 32) {
+            const int j = p / hp, q = p - j * hp;
+            float n0, n1;
+            normal_pair(key, e.vox_offset + w, stream_pair(j, 2 * q, S), n0, n1);
+            rows[2 * q].eps[j] = n0;
+            if (2 * q + 1 < S) rows[2 * q + 1].eps[j] = n1;
+        }
+    }
+    __syncwarp();
     if (lane < S) {
+        VS vs;
+        vs.load_rows(e, st_sm, 1);
+        typename VS::Terms tm;
+        vs.prior_terms(e, ec, tm);
         const int s = lane;
         Row &r = rows[s];
         float eps[N], th[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j)
-            eps[j] = (!LEAN && e.eps) ? e.eps[((int64_t)j * S + s) * e.ld + w] : normal_at(key, e.vox_offset + w, j, s, S);
+        for (int j = 0; j < N; ++j) eps[j] = r.eps[j];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             float v = vs.mu[i] + tm.sd[i] * eps[i];
@@ -193,8 +268,6 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
             r.x[p] = x[p];
             r.dx[p] = dxp;
         }
-#pragma unroll
-        for (int j = 0; j < N; ++j) r.eps[j] = eps[j];
         // noise and latent-loss terms of this sample (voxel_step.h: sample loop)
         const float thn = th[N - 1];
         const float inv_nv = fexp(-thn);
@@ -267,12 +340,18 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
         if (lane < S) { off_a[lane + 1] = ia; off_b[lane + 1] = ib; }
         if (lane == 0) { off_a[0] = 0; off_b[0] = 0; }
     }
-    __syncwarp();
+    dw_phase_sync();
     const int total_a = off_a[S], total_b = off_b[S];
+    if (lane < S) {                                            // every sample lists its own items
+        unsigned short *ma = imap_a + off_a[lane], *mb = imap + off_b[lane];
+        for (int k = 0; k < my_small; ++k) ma[k] = (unsigned short)((lane << 6) | k);
+        for (int k = 0; k < my_npts; ++k) mb[k] = (unsigned short)((lane << 6) | k);
+    }
+    __syncwarp();
 
     // ---- phase 1: series for the grid points with x <= 2 ----
     for (int idx = lane; idx < total_a; idx += 32) {
-        const int s = dw_find(off_a, S, idx), k = idx - off_a[s];
+        const int s = imap_a[idx] >> 6, k = imap_a[idx] & 63;
         const Row &r = rows[s];
         const float u = r.u0 + (float)k * h, x = r.s * u;
         float Pv = 0.0f, Jv = 0.0f;
@@ -280,7 +359,7 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
         P1[s * nt + k] = Pv;
         J1[s * nt + k] = Jv;
     }
-    __syncwarp();
+    dw_phase_sync();
 
     // ---- phase 2: density, quadrature increments, running P and J along each sample's grid ----
     {
@@ -288,7 +367,8 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
         for (int r0 = 0; r0 < total_b; r0 += 32) {
             const int idx = r0 + lane;
             const bool valid = idx < total_b;
-            const int s = valid ? dw_find(off_b, S, idx) : 0, k = valid ? idx - off_b[s] : 0;
+            const int sk = valid ? (int)imap[idx] : 0;
+            const int s = sk >> 6, k = sk & 63;
             const Row &r = rows[s];
             const float u = r.u0 + (float)k * h, x = r.s * u;
             const float lnx = r.ln_s + flog(fmax2(u, 1e-30f));
@@ -299,12 +379,22 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
                 if (k >= r.nsmall) {
                     if (r.absmode) {
                         float Q, dQa, dQx;
-                        igammac_d(r.g, x, lnx, Q, dQa, dQx);
+                        igammac_d_slow(r.g, x, lnx, Q, dQa, dQx);
                         P1[s * nt + k] = 1.0f - Q;
                         J1[s * nt + k] = r.g.psi_a * (1.0f - Q) - dQa;
                     } else {
                         const float xp = k > 0 ? r.s * (r.u0 + (float)(k - 1) * h) : 0.0f;
-                        gamma_quad(r.g, fmax2(xp, 2.0f), x, r.nq, vP, vJ);
+                        const float from = fmax2(xp, 2.0f);
+                        if (x - from <= (float)r.nq) {
+                            gamma_quad(r.g, from, x, r.nq, vP, vJ);
+                        } else {
+                            // first point of a sample whose bolus arrived before t = 0 (delt < 0: u0 > h): too wide
+                            // for the sample's piece count - evaluate afresh, expressed as the increment over P(a, 2)
+                            float Q, dQa, dQx;
+                            igammac_d_slow(r.g, x, lnx, Q, dQa, dQx);
+                            vP = (1.0f - Q) - r.P2;
+                            vJ = (r.g.psi_a * (1.0f - Q) - dQa) - r.J2;
+                        }
                         inc = true;
                     }
                 }
@@ -324,7 +414,7 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
             carryJ = __shfl_sync(FULL, vJ, 31);
         }
     }
-    __syncwarp();
+    dw_phase_sync();
 
     // ---- phase 3: AIF on the grid, tissue recurrence as a weighted segmented scan ----
     {
@@ -337,7 +427,8 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
         for (int r0 = 0; r0 < total_b; r0 += 32) {
             const int idx = r0 + lane;
             const bool valid = idx < total_b;
-            const int s = valid ? dw_find(off_b, S, idx) : 0, k = valid ? idx - off_b[s] : 0;
+            const int sk = valid ? (int)imap[idx] : 0;
+            const int s = sk >> 6, k = sk & 63;
             const Row &r = rows[s];
             float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             if (valid) {
@@ -351,6 +442,10 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
                     q2 = 1.0f - Pb;
                     q2a = r.g.psi_a * Pb - Jb;
                     q2x = -D1[s * nt + k2];
+                } else if (u - tau > 0.0f) {
+                    // delt < 0: the bolus ended after t = 0 but began before the grid does; no grid value to reuse
+                    const float u2 = u - tau;
+                    igammac_d_slow(r.g, r.s * u2, r.ln_s + flog(u2), q2, q2a, q2x);
                 }
                 const bool dead = (md.flags & SVBASL_F_DISP_ASWRITTEN) && ti > r.delt + tau;   // aslrest_disp.py:108
                 if (!dead) {
@@ -375,15 +470,17 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
 #pragma unroll
                 for (int z = 0; z < 4; ++z) c[z] += rho_l1 * carry[z];
             }
-            if (valid) {
+            const int ia = r.i0 + k;                                 // absolute grid index
+            if (valid && ia >= 0 && ((need >> ia) & 1ull)) {
+                const int slot = __popcll(need & ((1ull << ia) - 1ull));
 #pragma unroll
-                for (int z = 0; z < 4; ++z) CC[((size_t)z * S + s) * nt + k] = c[z];
+                for (int z = 0; z < 4; ++z) CC[((size_t)z * S + s) * nslot + slot] = c[z];
             }
 #pragma unroll
             for (int z = 0; z < 4; ++z) carry[z] = __shfl_sync(FULL, c[z], 31);
         }
     }
-    __syncwarp();
+    dw_phase_sync();
 
     // ---- phase 4: lane = (sample, time point): tissue interpolation, arterial AIF, residual, gradient sums ----
     for (int idx = lane; idx < S * nb; idx += 32) {
@@ -394,14 +491,15 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
 #pragma unroll
         for (int p = 0; p < P; ++p) d[p] = 0.0f;
         {
-            const int klo = sm_lo[b] - r.i0;
+            const int lo = sm_lo[b], klo = lo - r.i0;
             const float fr = sm_fr[b];
+            const int slot0 = __popcll(need & ((1ull << lo) - 1ull));      // lo + 1 is needed too: the next slot
             float Sv[4];
 #pragma unroll
             for (int z = 0; z < 4; ++z) {
-                const float *cz = CC + ((size_t)z * S + s) * nt;
-                const float c0 = (klo >= 0 && klo < r.npts) ? cz[klo] : 0.0f;
-                const float c1 = (klo + 1 >= 0 && klo + 1 < r.npts) ? cz[klo + 1] : 0.0f;
+                const float *cz = CC + ((size_t)z * S + s) * nslot;
+                const float c0 = (klo >= 0 && klo < r.npts) ? cz[slot0] : 0.0f;
+                const float c1 = (klo + 1 >= 0 && klo + 1 < r.npts) ? cz[slot0 + 1] : 0.0f;
                 Sv[z] = c0 + fr * (c1 - c0);
             }
             pred = r.pvf * Sv[0];
@@ -430,7 +528,7 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
                     float Pv, Jv;
                     if (r.absmode || kk >= r.npts) {
                         float Q, dQa, dQx;
-                        igammac_d(r.g, x, lnx, Q, dQa, dQx);
+                        igammac_d_slow(r.g, x, lnx, Q, dQa, dQx);
                         Pv = 1.0f - Q;
                         Jv = r.g.psi_a * Pv - dQa;
                     } else {
@@ -438,9 +536,16 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
                         float from, Pb, Jb;
                         bool quad = true;
                         if (kk >= 0 && xb >= 2.0f) { from = xb; Pb = P1[s * nt + kk]; Jb = J1[s * nt + kk]; }
-                        else if (x <= 2.0f) { gamma_series14(r.g, x, lnx, Pb, Jb); from = x; quad = false; }
+                        else if (x <= 2.0f) { gamma_series14_slow(r.g, x, lnx, Pb, Jb); from = x; quad = false; }
                         else { from = 2.0f; Pb = r.P2; Jb = r.J2; }
                         float dP = 0.0f, dJ = 0.0f;
+                        if (quad && x - from > (float)r.nq) {           // wide gap below the first grid point (delt < 0)
+                            float Q, dQa, dQx;
+                            igammac_d_slow(r.g, x, lnx, Q, dQa, dQx);
+                            Pb = 1.0f - Q;
+                            Jb = r.g.psi_a * Pb - dQa;
+                            quad = false;
+                        }
                         if (quad) gamma_quad(r.g, from, x, r.nq, dP, dJ);
                         Pv = Pb + dP;
                         Jv = Jb + dJ;
@@ -480,29 +585,59 @@ __global__ void __launch_bounds__(32 * kDwWarps, 3) disp_warp_kernel(const __gri
         }
     }
 
-    // ---- phase 5: sums over the lanes (every lane ends with the totals), closing algebra, update ----
+    // ---- phase 5: sums over the lanes through a shared-memory tile, closing algebra, update ----
+    {
+        constexpr int NV = DwLayout<M>::NV;
+        float *tile = P1, *tots = P1 + NV * 33;                 // P1 / J1 / D1 are no longer needed
+        dw_phase_sync();
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+        for (int i = 0; i < N; ++i) { tile[i * 33 + lane] = pa_mu[i]; tile[(N + i) * 33 + lane] = pa_hyp[i]; }
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            pa_mu[i] += __shfl_xor_sync(FULL, pa_mu[i], o);
-            pa_hyp[i] += __shfl_xor_sync(FULL, pa_hyp[i], o);
+        for (int k = 0; k < NT; ++k) tile[(2 * N + k) * 33 + lane] = pa_L[k];
+        tile[(NV - 1) * 33 + lane] = pcost;
+        __syncwarp();
+        for (int q = lane; q < NV; q += 32) {
+            const float *row = tile + q * 33;
+            float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;   // same order on every launch: bit-reproducible
+#pragma unroll
+            for (int l = 0; l < 32; l += 4) { t0 += row[l]; t1 += row[l + 1]; t2 += row[l + 2]; t3 += row[l + 3]; }
+            tots[q] = (t0 + t1) + (t2 + t3);
         }
+        __syncwarp();
 #pragma unroll
-        for (int k = 0; k < NT; ++k) pa_L[k] += __shfl_xor_sync(FULL, pa_L[k], o);
-        pcost += __shfl_xor_sync(FULL, pcost, o);
+        for (int i = 0; i < N; ++i) { pa_mu[i] = tots[i]; pa_hyp[i] = tots[N + i]; }
+#pragma unroll
+        for (int k = 0; k < NT; ++k) pa_L[k] = tots[2 * N + k];
+        pcost = tots[NV - 1];
     }
+    VS vs;
+    vs.load_rows(e, st_sm, 1);
+    typename VS::Terms tm;
+    vs.prior_terms(e, ec, tm);
     float cost = vs.finish(e, ec, tm, pa_mu, pa_L, pa_hyp, pcost, numeric);
     int skipped = 0;
     if (live) {
         if (!LEAN && a.cost) a.cost[w] = cost;
         if (!LEAN && a.grad) vs.store_grads(e, a.grad, w);
         if (update) {
-            if (vs.grads_finite() && cost == cost) {
-                vs.adam_update(e, a.ad, a.ad.lr_t[step], w, true, a.ad.m + w, a.ad.v + w, e.ld, a.ad.m + w, a.ad.v + w, e.ld);
-            } else {
+            // TF-Adam, one state row per lane (the gradient rows go through shared memory in state order)
+            const bool ok = vs.grads_finite() && cost == cost;
+            if (lane == 0) vs.store_grad_rows(e, g_sm, 1);
+            __syncwarp();
+            float *so = (e.state_out ? e.state_out : e.state) + w;
+            const float lr_t = a.ad.lr_t[step];
+            for (int r = lane; r < n_state; r += 32) {
+                if (ok) {
+                    float mm = m_sm[r], vv = v_sm[r];
+                    so[(int64_t)r * e.ld] = VS::adam1(a.ad, lr_t, st_sm[r], g_sm[r], mm, vv);
+                    a.ad.m[(int64_t)r * e.ld + w] = mm;
+                    a.ad.v[(int64_t)r * e.ld + w] = vv;
+                } else if (e.state_out && e.state_out != e.state) {
+                    so[(int64_t)r * e.ld] = st_sm[r];
+                }
+            }
+            if (!ok) {
                 skipped = lane == 0 ? 1 : 0;
-                vs.store_state(e, w);
                 cost = 0.0f;
             }
         }
@@ -540,7 +675,7 @@ template <class M, int FL>
 int launch_step_disp_warp(const StepArgs &a, cudaStream_t st) {
     const unsigned grid = (unsigned)((a.e.n_vox + kDwWarps - 1) / kDwWarps);
     if (grid == 0) return 0;
-    const size_t smem = sizeof(float) * kDwWarps * DwLayout<M>::floats(a.e.n_samples, a.md.conv_nt);
+    const size_t smem = sizeof(float) * kDwWarps * DwLayout<M>::floats(a.e.n_samples, a.md.conv_nt, a.e.n_batch);
     if (smem > 48 * 1024) {
         static std::atomic<int> granted[kMaxDevices];
         int dev = 0;

@@ -136,21 +136,23 @@ struct VoxelStep {
     float g_mu[N], g_lv[N], g_od[NL > 0 ? NL : 1], g_lphi[N];
     float ak_out[N];                                // share of d(sum cost)/d(log ak) of spatial parameter i
 
-    SVB_HD void load(const svbasl_engine &e, int64_t w) {
-        const float *s = e.state + w;
+    SVB_HD void load(const svbasl_engine &e, int64_t w) { load_rows(e, e.state + w, e.ld); }
+
+    // state rows of one voxel from `s` with row stride `ld` (global memory, or a staged copy)
+    SVB_HD void load_rows(const svbasl_engine &e, const float *s, int64_t ld) {
         int n_ard = 0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            mu[i] = s[(int64_t)i * e.ld];
-            lv[i] = s[(int64_t)(N + i) * e.ld];
+            mu[i] = s[(int64_t)i * ld];
+            lv[i] = s[(int64_t)(N + i) * ld];
             lphi[i] = 0.0f;
         }
 #pragma unroll
-        for (int k = 0; k < NL; ++k) od[k] = s[(int64_t)(2 * N + k) * e.ld];
+        for (int k = 0; k < NL; ++k) od[k] = s[(int64_t)(2 * N + k) * ld];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             if (e.prior_type[i] == SVBASL_PRIOR_ARD) {
-                lphi[i] = s[(int64_t)(2 * N + NL + n_ard) * e.ld];
+                lphi[i] = s[(int64_t)(2 * N + NL + n_ard) * ld];
                 ++n_ard;
             }
         }
@@ -388,19 +390,20 @@ struct VoxelStep {
         return acc == 0.0f;               // NaN/Inf * 0 = NaN
     }
 
-    SVB_HD void store_grads(const svbasl_engine &e, float *grad, int64_t w) const {
-        float *g = grad + w;
+    SVB_HD void store_grads(const svbasl_engine &e, float *grad, int64_t w) const { store_grad_rows(e, grad + w, e.ld); }
+
+    SVB_HD void store_grad_rows(const svbasl_engine &e, float *g, int64_t ld) const {
         int a = 0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            g[(int64_t)i * e.ld] = g_mu[i];
-            g[(int64_t)(N + i) * e.ld] = g_lv[i];
+            g[(int64_t)i * ld] = g_mu[i];
+            g[(int64_t)(N + i) * ld] = g_lv[i];
         }
 #pragma unroll
-        for (int k = 0; k < NL; ++k) g[(int64_t)(2 * N + k) * e.ld] = g_od[k];
+        for (int k = 0; k < NL; ++k) g[(int64_t)(2 * N + k) * ld] = g_od[k];
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            if (e.prior_type[i] == SVBASL_PRIOR_ARD) g[(int64_t)(2 * N + NL + a++) * e.ld] = g_lphi[i];
+            if (e.prior_type[i] == SVBASL_PRIOR_ARD) g[(int64_t)(2 * N + NL + a++) * ld] = g_lphi[i];
     }
 
     static SVB_HD float adam1(const svbasl_adam &ad, float lr_t, float x, float g, float &m, float &v) {
