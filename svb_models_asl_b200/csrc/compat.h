@@ -34,6 +34,12 @@ SVB_D float ftanh(float x) {                               // 1 - 2/(exp(2x)+1):
     return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 SVB_D bool finite_f(float x) { return isfinite(x); }
+// tanh(z) from zc = 2 log2(e) z: 1 - 2 / (2^zc + 1) - MUFU.EX2, FADD, MUFU.RCP, FFMA
+SVB_D float ftanh_c(float zc) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(zc));
+    return fmaf(-2.0f, __fdividef(1.0f, e + 1.0f), 1.0f);
+}
 #else
 SVB_HD float fexp(float x) { return expf(x); }
 SVB_HD float fexp2(float x) { return exp2f(x); }
@@ -50,6 +56,7 @@ SVB_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a
 SVB_HD float ferf(float x) { return erff(x); }
 SVB_HD float ftanh(float x) { return tanhf(x); }
 SVB_HD bool finite_f(float x) { return isfinite(x); }
+SVB_HD float ftanh_c(float zc) { return tanhf(zc * 0.34657359027997264f); }       // zc / (2 log2 e)
 #endif
 
 // Wait until this thread's asynchronous global->shared copies (kernels.cuh: Adam moments, neighbour tile) have

@@ -62,6 +62,13 @@ struct NNWeights {                    // aslnn.py:238-240, row-major as in the .
     float w0[2][SVBASL_NN_HIDDEN], b0[SVBASL_NN_HIDDEN];
     float w1[SVBASL_NN_HIDDEN][SVBASL_NN_HIDDEN], b1[SVBASL_NN_HIDDEN];
     float w2[SVBASL_NN_HIDDEN], b2;
+    // Folded forms for the fused kernels (model_nn.h).  tanh(z) = 1 - 2 / (2^(c z) + 1) with c = 2 log2(e): the
+    // pre-activations are produced already multiplied by c (weights and biases scaled on the host), so a tanh is
+    // MUFU.EX2, FADD, MUFU.RCP, FFMA; and the delttiss-derivative of layer 2's pre-activation,
+    // sum_j W1[j][k] (1 - h_j^2) W0[1][j], takes its constant factor from w1d[j][k] = W0[1][j] W1[j][k].
+    float w0t_c[SVBASL_NN_HIDDEN], w0d_c[SVBASL_NN_HIDDEN], b0_c[SVBASL_NN_HIDDEN];      // c W0[0][j], c W0[1][j], c b0[j]
+    float w1_c[SVBASL_NN_HIDDEN][SVBASL_NN_HIDDEN], b1_c[SVBASL_NN_HIDDEN];              // c W1[j][k], c b1[k]
+    float w1d[SVBASL_NN_HIDDEN][SVBASL_NN_HIDDEN];
 };
 
 struct DevModel {
@@ -122,6 +129,17 @@ inline DevModel make_dev_model(const svbasl_model &m) {
         for (int j = 0; j < H; ++j) d.nn.b1[j] = *p++;
         for (int j = 0; j < H; ++j) d.nn.w2[j] = *p++;
         d.nn.b2 = *p++;
+        const float c = 2.8853900817779268f;                              // 2 log2(e)
+        for (int j = 0; j < H; ++j) {
+            d.nn.w0t_c[j] = c * d.nn.w0[0][j];
+            d.nn.w0d_c[j] = c * d.nn.w0[1][j];
+            d.nn.b0_c[j] = c * d.nn.b0[j];
+            d.nn.b1_c[j] = c * d.nn.b1[j];
+            for (int k = 0; k < H; ++k) {
+                d.nn.w1_c[j][k] = c * d.nn.w1[j][k];
+                d.nn.w1d[j][k] = d.nn.w0[1][j] * d.nn.w1[j][k];
+            }
+        }
     } else {
         d.nn = NNWeights();
     }

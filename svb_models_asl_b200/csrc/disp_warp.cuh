@@ -36,10 +36,7 @@ namespace svb {
 #ifndef SVB_DW_PHASE_BARRIER
 #define SVB_DW_PHASE_BARRIER 1
 #endif
-#ifndef SVB_DW_WARPS
-#define SVB_DW_WARPS 8
-#endif
-constexpr int kDwWarps = SVB_DW_WARPS;    // voxels (warps) per CTA; the warps of a CTA walk the phases together
+constexpr int kDwWarpsDefault = 8;        // voxels (warps) per CTA; the warps of a CTA walk the phases together
 constexpr int kDwNtMax = 64;              // convolution grid points supported
 constexpr int kDwBMax = 32;               // time points per batch supported (lane = time point)
 constexpr int kDwSMax = 32;               // samples supported (lane = sample)
@@ -131,7 +128,7 @@ __device__ __forceinline__ int dw_find(const int *off, int S, int idx) {
     return s;
 }
 
-template <class M, int FL>
+template <class M, int FL, int kDwWarps>
 __global__ void __launch_bounds__(32 * kDwWarps, 16 / kDwWarps) disp_warp_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ float dw_smem[];
     __shared__ float red[kDwWarps];
@@ -671,7 +668,7 @@ inline bool disp_warp_eligible(const StepArgs &a, bool tissue) {
     return true;
 }
 
-template <class M, int FL>
+template <class M, int FL, int kDwWarps>
 int launch_step_disp_warp(const StepArgs &a, cudaStream_t st) {
     const unsigned grid = (unsigned)((a.e.n_vox + kDwWarps - 1) / kDwWarps);
     if (grid == 0) return 0;
@@ -685,10 +682,10 @@ int launch_step_disp_warp(const StepArgs &a, cudaStream_t st) {
             int optin = 0;
             cudaFuncAttributes fa;
             cudaError_t err = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev < 0 ? 0 : dev);
-            if (err == cudaSuccess) err = cudaFuncGetAttributes(&fa, disp_warp_kernel<M, FL>);
+            if (err == cudaSuccess) err = cudaFuncGetAttributes(&fa, disp_warp_kernel<M, FL, kDwWarps>);
             if (err == cudaSuccess) {
                 have = optin - (int)fa.sharedSizeBytes;
-                err = cudaFuncSetAttribute(disp_warp_kernel<M, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, have);
+                err = cudaFuncSetAttribute(disp_warp_kernel<M, FL, kDwWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, have);
             }
             if (err != cudaSuccess) {
                 set_error("disp_warp_kernel: cannot opt in to large shared memory: %s", cudaGetErrorString(err));
@@ -696,9 +693,9 @@ int launch_step_disp_warp(const StepArgs &a, cudaStream_t st) {
             }
             if (dev >= 0) granted[dev].store(have, std::memory_order_release);
         }
-        if ((size_t)have < smem) return 1;                         // does not fit: caller falls back to the scalar kernel
+        if ((size_t)have < smem) return 1;                         // does not fit: caller tries fewer warps / the scalar kernel
     }
-    disp_warp_kernel<M, FL><<<grid, 32 * kDwWarps, smem, st>>>(a);
+    disp_warp_kernel<M, FL, kDwWarps><<<grid, 32 * kDwWarps, smem, st>>>(a);
     return check_launch("disp_warp_kernel");
 }
 
@@ -707,7 +704,12 @@ template <class M, int FL>
 int launch_step_disp(const StepArgs &a, cudaStream_t st) {
     const bool force_scalar = getenv("SVBASL_DISP_SCALAR") != nullptr;              // tests compare the two kernels
     if (!force_scalar && disp_warp_eligible(a, M::TISS)) {
-        const int rc = launch_step_disp_warp<M, FL>(a, st);
+        // 8 warps per CTA (two CTAs per SM); 4 when the per-warp tables of a large S / grid / batch do not fit
+        const char *wenv = getenv("SVBASL_DW_WARPS");               // measurement switch
+        int rc = 1;
+        if (wenv && wenv[0] == '1' && wenv[1] == '6') rc = launch_step_disp_warp<M, FL, 16>(a, st);
+        if (rc > 0 && !(wenv && wenv[0] == '4')) rc = launch_step_disp_warp<M, FL, kDwWarpsDefault>(a, st);
+        if (rc > 0) rc = launch_step_disp_warp<M, FL, 4>(a, st);
         if (rc <= 0) return rc;
     }
     return launch_step<M, 0, FL>(a, st);

@@ -23,7 +23,7 @@ struct AslNN {
     struct Vox {};
     struct Sample {
         float f;
-        float a1[H];      // W0[1][j]*delt + b0[j]
+        float a1[H];      // c (W0[1][j] delt + b0[j]), c = 2 log2(e): the delttiss part of layer 1's scaled pre-activation
     };
 
     template <class Acc>
@@ -35,31 +35,33 @@ struct AslNN {
         s.f = x[0];
         const NNWeights &w = m.nn;
 #pragma unroll
-        for (int j = 0; j < H; ++j) s.a1[j] = w.w0[1][j] * x[1] + w.b0[j];
+        for (int j = 0; j < H; ++j) s.a1[j] = w.w0d_c[j] * x[1] + w.b0_c[j];
         return s;
     }
 
+    // Per row: 10 FFMA + 10 tanh (layer 1), 10 FFMA (1 - h^2), 200 FFMA (the two 10x10 products), 10 tanh, 40 for
+    // the output layer and its derivative: ~310 FP32-pipe + 40 MUFU instructions (profiles/r2_notes.md section 4).
     static SVB_HD void eval(const DevModel &m, const Sample &s, float t, float &pred, float *d) {
         const NNWeights &w = m.nn;
-        float h1[H], dh1[H];
+        float h1[H], g1[H];
 #pragma unroll
         for (int j = 0; j < H; ++j) {
-            const float h = ftanh(w.w0[0][j] * t + s.a1[j]);
+            const float h = ftanh_c(w.w0t_c[j] * t + s.a1[j]);
             h1[j] = h;
-            dh1[j] = (1.0f - h * h) * w.w0[1][j];
+            g1[j] = 1.0f - h * h;
         }
         float out = w.b2, dout = 0.0f;
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-            float z = w.b1[k], dz = 0.0f;
+            float z = w.b1_c[k], dz = 0.0f;
 #pragma unroll
             for (int j = 0; j < H; ++j) {
-                z += w.w1[j][k] * h1[j];
-                dz += w.w1[j][k] * dh1[j];
+                z += w.w1_c[j][k] * h1[j];
+                dz += w.w1d[j][k] * g1[j];
             }
-            const float h = ftanh(z);
+            const float h = ftanh_c(z);
             out += w.w2[k] * h;
-            dout += w.w2[k] * (1.0f - h * h) * dz;
+            dout += (w.w2[k] * dz) * (1.0f - h * h);
         }
         pred = s.f * out;
         d[0] = out;

@@ -399,3 +399,41 @@ def test_fused_spatial_iteration_follows_the_oracle(use_graph, record_error):
     assert lak_err <= 1e-4, lak_err
     costs = f.cost_hist[:n_it].cpu().numpy()
     assert np.isfinite(costs).all() and (costs != 0).all()
+
+
+def test_device_resident_setup_equals_host_setup():
+    """SvbFit.setup_from_device (data already on the GPU, low-rank time points, neighbour rows of the local range only
+    - what bench.py's 10 M-voxel volume goes through) sets up the same fit as the host-array path of train(): same
+    initial posterior, same state and log ak after 12 iterations with a spatial prior."""
+    from svb import DataModel
+    from svb_models_asl import AslRestModel
+    from svb_models_asl_b200.sharding import ShardPlan
+    from svb_models_asl_b200.svbcompat.fit import SvbFit
+    rng = np.random.default_rng(23)
+    shape = (7, 6, 5)
+    vol, _f, _d = _sim_volume(shape, rng, repeats=8, noise=1.0, t1b=1.65, slicedt=0.0452)
+    over = {"ftiss": {"prior_type": "M"}}
+    opts = dict(tau=1.8, casl=True, plds=PLDS, repeats=[8], slicedt=0.0452, param_overrides=over)
+    results = []
+    for route in ("host", "device"):
+        dm = DataModel(vol) if route == "host" else DataModel.header(shape, 48)
+        model = AslRestModel(dm, **opts)
+        fit = SvbFit(dm, model)
+        if route == "host":
+            fit._setup(model.tpts(), dm.data_flattened, 6, 10, 0.01, epochs=4, force_num_latent_loss=True, param_overrides=over)
+            f = fit.fused
+        else:
+            plan = ShardPlan(dm.n_nodes, 0, 1, dm.neighbour_table)
+            dev = torch.device("cuda:0")
+            data = torch.as_tensor(vol.reshape(-1, 48).T.copy(), device=dev)
+            ti, zoff = model.tpts_lowrank()
+            f = fit.setup_from_device(data, plan, ti, torch.as_tensor(zoff, device=dev), 6, 10, 0.01, 40, param_overrides=over)
+        init = f.state.cpu().numpy().copy()
+        for _ in range(12):
+            f.step()
+        f.check_peers()
+        results.append((init, f.state.cpu().numpy(), float(f.log_ak[0])))
+        f.release()
+    np.testing.assert_allclose(results[1][0], results[0][0], rtol=2e-6, atol=1e-6)      # initial posterior
+    np.testing.assert_allclose(results[1][1], results[0][1], rtol=2e-4, atol=2e-5)      # full [T, W] time points vs ti + zoff
+    assert results[1][2] == pytest.approx(results[0][2], rel=1e-5)
