@@ -66,9 +66,14 @@ struct NNWeights {                    // aslnn.py:238-240, row-major as in the .
     // pre-activations are produced already multiplied by c (weights and biases scaled on the host), so a tanh is
     // MUFU.EX2, FADD, MUFU.RCP, FFMA; and the delttiss-derivative of layer 2's pre-activation,
     // sum_j W1[j][k] (1 - h_j^2) W0[1][j], takes its constant factor from w1d[j][k] = W0[1][j] W1[j][k].
+    // The two 10x10 tables are stored [k][j] (the FFMA chain of one output unit k reads a contiguous row) in rows of
+    // 12 floats on a 16-byte boundary: sm_100 has no constant-bank operand on FFMA, weights reach the FP32 pipe through
+    // uniform registers, and only contiguous, aligned constants load four at a time (LDCU.128) - 60 loads per row of
+    // the network instead of 200, each of which costs an issue slot (profiles/r2_notes.md section 4).
     float w0t_c[SVBASL_NN_HIDDEN], w0d_c[SVBASL_NN_HIDDEN], b0_c[SVBASL_NN_HIDDEN];      // c W0[0][j], c W0[1][j], c b0[j]
-    float w1_c[SVBASL_NN_HIDDEN][SVBASL_NN_HIDDEN], b1_c[SVBASL_NN_HIDDEN];              // c W1[j][k], c b1[k]
-    float w1d[SVBASL_NN_HIDDEN][SVBASL_NN_HIDDEN];
+    float b1_c[SVBASL_NN_HIDDEN];                                                          // c b1[k]
+    alignas(16) float w1_c[SVBASL_NN_HIDDEN][12];                                          // [k][j] = c W1[j][k]
+    alignas(16) float w1d[SVBASL_NN_HIDDEN][12];                                           // [k][j] = W0[1][j] W1[j][k]
 };
 
 struct DevModel {
@@ -136,8 +141,8 @@ inline DevModel make_dev_model(const svbasl_model &m) {
             d.nn.b0_c[j] = c * d.nn.b0[j];
             d.nn.b1_c[j] = c * d.nn.b1[j];
             for (int k = 0; k < H; ++k) {
-                d.nn.w1_c[j][k] = c * d.nn.w1[j][k];
-                d.nn.w1d[j][k] = d.nn.w0[1][j] * d.nn.w1[j][k];
+                d.nn.w1_c[k][j] = c * d.nn.w1[j][k];
+                d.nn.w1d[k][j] = d.nn.w0[1][j] * d.nn.w1[j][k];
             }
         }
     } else {

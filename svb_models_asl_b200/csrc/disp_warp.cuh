@@ -36,6 +36,7 @@ namespace svb {
 #ifndef SVB_DW_PHASE_BARRIER
 #define SVB_DW_PHASE_BARRIER 1
 #endif
+constexpr int kDwTuneDefault = 8;         // CTA-wide barriers (bits 1, 2, 4, 8 = after phases 1, 2, 3, before 5): measured best
 constexpr int kDwWarpsDefault = 8;        // voxels (warps) per CTA; the warps of a CTA walk the phases together
 constexpr int kDwNtMax = 64;              // convolution grid points supported
 constexpr int kDwBMax = 32;               // time points per batch supported (lane = time point)
@@ -76,7 +77,7 @@ static __device__ __noinline__ void gamma_series14_slow(const GammaConst &g, flo
 
 template <int N, int P>
 struct DwRow {                            // per-sample table row (shared memory)
-    float x[P > 0 ? P : 1], dx[P > 0 ? P : 1], eps[N];
+    float x[P > 0 ? P : 1], dx[P > 0 ? P : 1], eps[N], th[N];
     float s, ln_s, sp_live, kct, kcb, delt, deltb, u0, P2, J2, wres, fb, pvf;
     GammaConst g;
     int i0, npts, nsmall, nq, absmode;
@@ -112,6 +113,13 @@ __device__ __forceinline__ void dw_phase_sync() {
 #endif
 }
 
+// the same, the CTA-wide form selectable at run time (a.tune, identical for every thread): which phase boundaries are
+// worth a CTA barrier is a measurement question (waiting for the CTA's slowest warp against instruction-cache locality)
+__device__ __forceinline__ void dw_phase_sync_opt(int cta_wide) {
+    if (cta_wide) __syncthreads();
+    else __syncwarp();
+}
+
 __device__ __forceinline__ int warp_incl_scan_int(int v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -127,6 +135,37 @@ __device__ __forceinline__ int dw_find(const int *off, int S, int idx) {
     for (int q = 1; q < S; ++q) s += (idx >= off[q]) ? 1 : 0;
     return s;
 }
+
+// where a warp's tables live inside its slice of the dynamic shared memory
+template <class M>
+struct DwCarve {
+    typedef DwRow<M::P + 1, M::P> Row;
+    Row *rows;
+    float *P1, *J1, *D1, *CC, *sm_t, *sm_y, *sm_fr, *st_sm, *m_sm, *v_sm, *g_sm, *scal;
+    int *sm_lo, *off_a, *off_b;
+    unsigned short *imap, *imap_a;
+    __device__ __forceinline__ DwCarve(float *smem, int wv, int S, int nt, int nb) {
+        float *base = smem + (size_t)wv * DwLayout<M>::floats(S, nt, nb);
+        rows = reinterpret_cast<Row *>(base);
+        P1 = base + (sizeof(Row) * (size_t)S + 3) / 4;
+        J1 = P1 + (size_t)S * nt;
+        D1 = J1 + (size_t)S * nt;
+        CC = P1 + DwLayout<M>::grid_floats(S, nt);                                  // CC [4][S][2 nb]
+        sm_t = CC + (size_t)8 * S * nb;
+        sm_y = sm_t + kDwBMax;
+        sm_fr = sm_y + kDwBMax;
+        sm_lo = reinterpret_cast<int *>(sm_fr + kDwBMax);
+        off_a = sm_lo + kDwBMax;
+        off_b = off_a + kDwSMax + 1;
+        scal = reinterpret_cast<float *>(off_b + kDwSMax + 1);                      // 6 per-voxel scalars (last, tmax, pv)
+        imap = reinterpret_cast<unsigned short *>(off_b + kDwSMax + 1 + 6);         // item -> (s << 6) | k
+        imap_a = imap + (size_t)S * nt;                                             // the same for the x <= 2 list
+        st_sm = reinterpret_cast<float *>(imap_a + (size_t)S * nt);                 // staged state / m / v / grad rows
+        m_sm = st_sm + DwLayout<M>::kRowsMax;
+        v_sm = m_sm + DwLayout<M>::kRowsMax;
+        g_sm = v_sm + DwLayout<M>::kRowsMax;
+    }
+};
 
 template <class M, int FL, int kDwWarps>
 __global__ void __launch_bounds__(32 * kDwWarps, 16 / kDwWarps) disp_warp_kernel(const __grid_constant__ StepArgs a) {
@@ -149,19 +188,13 @@ __global__ void __launch_bounds__(32 * kDwWarps, 16 / kDwWarps) disp_warp_kernel
     const int mshift = (int)(tau * inv_h + 0.5f);              // tau / h, an integer (checked by the launcher)
 
     // ---- warp-private shared memory ----
-    float *base = dw_smem + (size_t)wip * DwLayout<M>::floats(S, nt, nb);
-    Row *rows = reinterpret_cast<Row *>(base);
-    float *P1 = base + (sizeof(Row) * (size_t)S + 3) / 4;
-    float *J1 = P1 + (size_t)S * nt, *D1 = J1 + (size_t)S * nt;
-    float *CC = P1 + DwLayout<M>::grid_floats(S, nt);                                          // CC [4][S][2 nb]
+    const DwCarve<M> cv(dw_smem, wip, S, nt, nb);
+    Row *rows = cv.rows;
+    float *P1 = cv.P1, *J1 = cv.J1, *D1 = cv.D1, *CC = cv.CC, *sm_t = cv.sm_t, *sm_y = cv.sm_y, *sm_fr = cv.sm_fr;
+    int *sm_lo = cv.sm_lo, *off_a = cv.off_a, *off_b = cv.off_b;
+    unsigned short *imap = cv.imap, *imap_a = cv.imap_a;
+    float *st_sm = cv.st_sm, *m_sm = cv.m_sm, *v_sm = cv.v_sm, *g_sm = cv.g_sm;
     const int nslot = 2 * nb;
-    float *sm_t = CC + (size_t)4 * S * nslot, *sm_y = sm_t + kDwBMax, *sm_fr = sm_y + kDwBMax;
-    int *sm_lo = reinterpret_cast<int *>(sm_fr + kDwBMax);
-    int *off_a = sm_lo + kDwBMax, *off_b = off_a + kDwSMax + 1;          // item offsets per sample (two lists)
-    unsigned short *imap = reinterpret_cast<unsigned short *>(off_b + kDwSMax + 1 + 6);      // item -> (s << 6) | k
-    unsigned short *imap_a = imap + (size_t)S * nt;                                           // the same for the x <= 2 list
-    float *st_sm = reinterpret_cast<float *>(imap_a + (size_t)S * nt);                        // staged state / m / v / grad rows
-    float *m_sm = st_sm + DwLayout<M>::kRowsMax, *v_sm = m_sm + DwLayout<M>::kRowsMax, *g_sm = v_sm + DwLayout<M>::kRowsMax;
     const int n_state = a.n_state;
     // the voxel's state and Adam moments: one row per lane, all in flight at once (the closing algebra reads them from
     // shared memory; row by row from global memory it was a chain of 2 x 36 dependent round trips)
@@ -236,23 +269,34 @@ __global__ void __launch_bounds__(32 * kDwWarps, 16 / kDwWarps) disp_warp_kernel
             if (2 * q + 1 < S) rows[2 * q + 1].eps[j] = n1;
         }
     }
-    __syncwarp();
-    if (lane < S) {
+    if (lane == 0) {
+        cv.scal[0] = __int_as_float(last);
+        cv.scal[1] = tmax;
+        cv.scal[2] = pv;
+    }
+    __syncthreads();
+    // ---- phase 0, packed over the CTA: thread = (voxel of the CTA, sample) ----
+    // One (voxel, sample) costs ~2,000 instructions here (theta, transforms, lgamma / digamma of the shape, the base
+    // series at x = 2, the sample's stretch of the grid) and a warp has only S samples for its 32 lanes; packed, the
+    // kDwWarps x S pairs of the CTA fill kDwWarps*S/32 warps instead of half-emptying all kDwWarps.
+    for (int t = threadIdx.x; t < kDwWarps * S; t += 32 * kDwWarps) {
+        const int wv = t / S, s = t - wv * S;
+        const DwCarve<M> co(dw_smem, wv, S, nt, nb);
+        Row &r = co.rows[s];
+        const int last_v = __float_as_int(co.scal[0]);
+        const float tmax_v = co.scal[1], pv_v = co.scal[2];
         VS vs;
-        vs.load_rows(e, st_sm, 1);
-        typename VS::Terms tm;
-        vs.prior_terms(e, ec, tm);
-        const int s = lane;
-        Row &r = rows[s];
+        vs.load_rows(e, co.st_sm, 1);
         float eps[N], th[N];
 #pragma unroll
         for (int j = 0; j < N; ++j) eps[j] = r.eps[j];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            float v = vs.mu[i] + tm.sd[i] * eps[i];
+            float v = vs.mu[i] + fexp(0.5f * vs.lv[i]) * eps[i];
 #pragma unroll
             for (int j = 0; j < i; ++j) v += vs.od[stri(i, j)] * eps[j];
             th[i] = v;
+            r.th[i] = v;
         }
         float x[P > 0 ? P : 1];
 #pragma unroll
@@ -265,11 +309,59 @@ __global__ void __launch_bounds__(32 * kDwWarps, 16 / kDwWarps) disp_warp_kernel
             r.x[p] = x[p];
             r.dx[p] = dxp;
         }
-        // noise and latent-loss terms of this sample (voxel_step.h: sample loop)
-        const float thn = th[N - 1];
-        const float inv_nv = fexp(-thn);
-        r.wres = ec.scale * inv_nv;
-        pcost += 0.5f * ec.t_full * thn;
+        r.wres = ec.scale * fexp(-th[N - 1]);
+        // dispersion constants (model_disp.h: prep_disp) and the sample's stretch of the grid
+        const float sv = M::DISP ? x[M::ix(M::I_S)] : md.s_fixed;
+        const float spv = M::DISP ? x[M::ix(M::I_SP)] : md.sp_fixed;
+        r.s = sv;
+        r.ln_s = flog(sv);
+        r.sp_live = spv < 10.0f ? 1.0f : 0.0f;
+        r.g = gamma_const(1.0f + fmin2(spv, 10.0f));
+        const float delt = M::ATT ? x[M::ix(M::I_DELT)] : md.att;
+        const float deltb = (M::I_DELTBLOOD >= 0) ? x[M::ix(M::I_DELTBLOOD)] : md.artt;
+        r.delt = delt;
+        r.deltb = deltb;
+        r.kct = M::CASL ? 2.0f * fexp(-delt * md.inv_t1b) : 0.0f;
+        r.kcb = M::CASL ? 2.0f * fexp(-deltb * md.inv_t1b) : 0.0f;
+        r.fb = M::ART ? x[M::ix(M::I_FBLOOD)] : 0.0f;
+        r.pvf = pv_v * x[M::ix(M::I_FTISS)];
+        const float p0 = delt * inv_h;
+        int i0 = p0 > (float)nt ? nt : (p0 > 0.0f ? (int)ceilf(p0) : 0);
+        if ((float)i0 * h - delt < 0.0f) ++i0;
+        else if (i0 > 0 && (float)(i0 - 1) * h - delt >= 0.0f) --i0;
+        r.i0 = i0;
+        r.u0 = (float)i0 * h - delt;
+        int last_s = last_v;
+        if (M::ART) {
+            // arterial arguments s (t_b - deltb) are looked up on this grid: extend it far enough
+            const float ext = (tmax_v - deltb + delt) * inv_h;
+            const int ie = ext > (float)nt ? nt : (ext > 0.0f ? (int)ext + 1 : 0);
+            last_s = ie > last_s ? ie : last_s;
+        }
+        last_s = last_s > nt - 1 ? nt - 1 : last_s;
+        const int npts = last_s - i0 + 1 > 0 ? last_s - i0 + 1 : 0;
+        r.npts = npts;
+        const float wmax = sv * h;
+        r.absmode = (wmax > 8.0f || !(wmax > 0.0f)) ? 1 : 0;      // wider than 8 (or degenerate): fresh evaluation per point
+        int nq = (int)ceilf(wmax);
+        r.nq = nq < 1 ? 1 : (nq > 8 ? 8 : nq);
+        int nsm = 0;
+        while (nsm < npts && sv * (r.u0 + (float)nsm * h) <= 2.0f) ++nsm;
+        r.nsmall = nsm;
+        gamma_series14(r.g, 2.0f, 0.6931471805599453f, r.P2, r.J2);
+    }
+    __syncthreads();
+    // the sample's latent-loss and noise terms (voxel_step.h: sample loop), lane = sample of this warp's voxel
+    if (lane < S) {
+        VS vs;
+        vs.load_rows(e, st_sm, 1);
+        typename VS::Terms tm;
+        vs.prior_terms(e, ec, tm);
+        const Row &r = rows[lane];
+        float eps[N], th[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) { eps[j] = r.eps[j]; th[j] = r.th[j]; }
+        pcost += 0.5f * ec.t_full * th[N - 1];
         float g[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) g[i] = 0.0f;
@@ -289,47 +381,8 @@ __global__ void __launch_bounds__(32 * kDwWarps, 16 / kDwWarps) disp_warp_kernel
 #pragma unroll
             for (int j = 0; j <= i; ++j) pa_L[tri(i, j)] += g[i] * eps[j];
         }
-        // dispersion constants (model_disp.h: prep_disp) and the sample's stretch of the grid
-        const float sv = M::DISP ? x[M::ix(M::I_S)] : md.s_fixed;
-        const float spv = M::DISP ? x[M::ix(M::I_SP)] : md.sp_fixed;
-        r.s = sv;
-        r.ln_s = flog(sv);
-        r.sp_live = spv < 10.0f ? 1.0f : 0.0f;
-        r.g = gamma_const(1.0f + fmin2(spv, 10.0f));
-        const float delt = M::ATT ? x[M::ix(M::I_DELT)] : md.att;
-        const float deltb = (M::I_DELTBLOOD >= 0) ? x[M::ix(M::I_DELTBLOOD)] : md.artt;
-        r.delt = delt;
-        r.deltb = deltb;
-        r.kct = M::CASL ? 2.0f * fexp(-delt * md.inv_t1b) : 0.0f;
-        r.kcb = M::CASL ? 2.0f * fexp(-deltb * md.inv_t1b) : 0.0f;
-        r.fb = M::ART ? x[M::ix(M::I_FBLOOD)] : 0.0f;
-        r.pvf = pv * x[M::ix(M::I_FTISS)];
-        const float p0 = delt * inv_h;
-        int i0 = p0 > (float)nt ? nt : (p0 > 0.0f ? (int)ceilf(p0) : 0);
-        if ((float)i0 * h - delt < 0.0f) ++i0;
-        else if (i0 > 0 && (float)(i0 - 1) * h - delt >= 0.0f) --i0;
-        r.i0 = i0;
-        r.u0 = (float)i0 * h - delt;
-        int last_s = last;
-        if (M::ART) {
-            // arterial arguments s (t_b - deltb) are looked up on this grid: extend it far enough
-            const float ext = (tmax - deltb + delt) * inv_h;
-            const int ie = ext > (float)nt ? nt : (ext > 0.0f ? (int)ext + 1 : 0);
-            last_s = ie > last_s ? ie : last_s;
-        }
-        last_s = last_s > nt - 1 ? nt - 1 : last_s;
-        const int npts = last_s - i0 + 1 > 0 ? last_s - i0 + 1 : 0;
-        r.npts = npts;
-        const float wmax = sv * h;
-        r.absmode = (wmax > 8.0f || !(wmax > 0.0f)) ? 1 : 0;      // wider than 8 (or degenerate): fresh evaluation per point
-        int nq = (int)ceilf(wmax);
-        r.nq = nq < 1 ? 1 : (nq > 8 ? 8 : nq);
-        int nsm = 0;
-        while (nsm < npts && sv * (r.u0 + (float)nsm * h) <= 2.0f) ++nsm;
-        r.nsmall = nsm;
-        gamma_series14(r.g, 2.0f, 0.6931471805599453f, r.P2, r.J2);
-        my_small = nsm;
-        my_npts = npts;
+        my_small = r.nsmall;
+        my_npts = r.npts;
     }
     // exclusive offsets of the two item lists
     {
@@ -356,7 +409,7 @@ __global__ void __launch_bounds__(32 * kDwWarps, 16 / kDwWarps) disp_warp_kernel
         P1[s * nt + k] = Pv;
         J1[s * nt + k] = Jv;
     }
-    dw_phase_sync();
+    dw_phase_sync_opt(a.tune & 1);
 
     // ---- phase 2: density, quadrature increments, running P and J along each sample's grid ----
     {
@@ -411,7 +464,7 @@ __global__ void __launch_bounds__(32 * kDwWarps, 16 / kDwWarps) disp_warp_kernel
             carryJ = __shfl_sync(FULL, vJ, 31);
         }
     }
-    dw_phase_sync();
+    dw_phase_sync_opt(a.tune & 2);
 
     // ---- phase 3: AIF on the grid, tissue recurrence as a weighted segmented scan ----
     {
@@ -477,7 +530,7 @@ __global__ void __launch_bounds__(32 * kDwWarps, 16 / kDwWarps) disp_warp_kernel
             for (int z = 0; z < 4; ++z) carry[z] = __shfl_sync(FULL, c[z], 31);
         }
     }
-    dw_phase_sync();
+    dw_phase_sync_opt(a.tune & 4);
 
     // ---- phase 4: lane = (sample, time point): tissue interpolation, arterial AIF, residual, gradient sums ----
     for (int idx = lane; idx < S * nb; idx += 32) {
@@ -586,7 +639,7 @@ __global__ void __launch_bounds__(32 * kDwWarps, 16 / kDwWarps) disp_warp_kernel
     {
         constexpr int NV = DwLayout<M>::NV;
         float *tile = P1, *tots = P1 + NV * 33;                 // P1 / J1 / D1 are no longer needed
-        dw_phase_sync();
+        dw_phase_sync_opt(a.tune & 8);
 #pragma unroll
         for (int i = 0; i < N; ++i) { tile[i * 33 + lane] = pa_mu[i]; tile[(N + i) * 33 + lane] = pa_hyp[i]; }
 #pragma unroll
@@ -695,7 +748,10 @@ int launch_step_disp_warp(const StepArgs &a, cudaStream_t st) {
         }
         if ((size_t)have < smem) return 1;                         // does not fit: caller tries fewer warps / the scalar kernel
     }
-    disp_warp_kernel<M, FL, kDwWarps><<<grid, 32 * kDwWarps, smem, st>>>(a);
+    StepArgs b = a;
+    const char *tune = getenv("SVBASL_DW_TUNE");                    // measurement switch: bit mask of CTA-wide phase barriers
+    b.tune = tune ? atoi(tune) : kDwTuneDefault;
+    disp_warp_kernel<M, FL, kDwWarps><<<grid, 32 * kDwWarps, smem, st>>>(b);
     return check_launch("disp_warp_kernel");
 }
 

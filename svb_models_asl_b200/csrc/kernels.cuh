@@ -29,6 +29,7 @@ struct StepArgs {
     double *cost_sum;        // [n_iters] or NULL
     long long *nan_count;    // [1] or NULL
     svbasl_hyper hy;         // fused tail of a spatial iteration; hy.done_ctas == NULL: none
+    int32_t tune;            // disp_warp_kernel: which phase boundaries are CTA-wide barriers
 };
 
 // Mailbox of one rank for the all-reduce of d(cost)/d(log ak) over NVLink peer memory: [2 parities][world] slots;

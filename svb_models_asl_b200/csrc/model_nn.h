@@ -56,8 +56,8 @@ struct AslNN {
             float z = w.b1_c[k], dz = 0.0f;
 #pragma unroll
             for (int j = 0; j < H; ++j) {
-                z += w.w1_c[j][k] * h1[j];
-                dz += w.w1d[j][k] * g1[j];
+                z += w.w1_c[k][j] * h1[j];
+                dz += w.w1d[k][j] * g1[j];
             }
             const float h = ftanh_c(z);
             out += w.w2[k] * h;
@@ -79,7 +79,9 @@ struct AslNN {
     static SVB_HD void run(const DevModel &m, const Vox &v, const float *x, Acc &acc) {
         Sample s = prep_sample(m, v, x);
         if (Acc::NB > 0) {
-#pragma unroll
+            // not unrolled: one row of the network is ~400 instructions and wants ~60 registers of its own; unrolling
+            // the time points only makes the compiler hoist weight loads across rows until it spills
+#pragma unroll 1
             for (int b = 0; b < (Acc::NB > 0 ? Acc::NB : 1); ++b) {
                 float pred, d[PA];
                 eval(m, s, acc.time(b), pred, d);
