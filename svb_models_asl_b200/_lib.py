@@ -16,8 +16,8 @@ MAX_SPATIAL = 4
 MAX_PEERS = 16
 
 MODEL_ASLREST, MODEL_ASLREST_DISP, MODEL_ASLNN = 0, 1, 2
-F_CASL, F_INFERATT, F_INFERART, F_INCWM, F_INFERWM, F_INFERT1, F_ARTONLY, F_DISP_INFER, F_DISP_ASWRITTEN = (
-    0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x100)
+F_CASL, F_INFERATT, F_INFERART, F_INCWM, F_INFERWM, F_INFERT1, F_ARTONLY, F_DISP_INFER, F_DISP_ASWRITTEN, F_NN_TC = (
+    0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x100, 0x200)
 XF_IDENTITY, XF_EXP, XF_ABS = 0, 1, 2
 PRIOR_N, PRIOR_ARD, PRIOR_MRF = 0, 1, 2
 LATENT_NUMERIC, LATENT_ANALYTIC = 0, 1

@@ -37,7 +37,7 @@ static uint32_t canonical_flags(const svbasl_model *m) {
         f &= (SVBASL_F_CASL | SVBASL_F_INFERATT | SVBASL_F_INFERART | SVBASL_F_ARTONLY | SVBASL_F_DISP_INFER);
         if (f & SVBASL_F_ARTONLY) f |= SVBASL_F_INFERART;
     } else if (m->kind == SVBASL_MODEL_ASLNN) {
-        f = 0;
+        f &= SVBASL_F_NN_TC;
     }
     return f;
 }
@@ -45,8 +45,9 @@ static uint32_t canonical_flags(const svbasl_model *m) {
 // Best kernel for (model layout, batch size): prefers the compile-time batch size, and the lean (production)
 // flavour when the call allows it.
 // `flavour`: 0 = generic only, 1 = lean allowed (no spatial prior in use), 2 = lean-spatial allowed.
-static const KernelEntry *find_entry(const svbasl_model *m, int nbt, bool want_eval, int flavour = 0) {
-    const uint32_t f = canonical_flags(m);
+static const KernelEntry *find_entry(const svbasl_model *m, int nbt, bool want_eval, int flavour = 0, bool allow_tc = true) {
+    uint32_t f = canonical_flags(m);
+    if (m->kind == SVBASL_MODEL_ASLNN && (want_eval || !allow_tc)) f &= ~(uint32_t)SVBASL_F_NN_TC;
     const KernelEntry *best = nullptr;
     int best_score = -1;
     for (int g = 0; g < kNumEntryGroups; ++g) {
@@ -62,6 +63,9 @@ static const KernelEntry *find_entry(const svbasl_model *m, int nbt, bool want_e
             if (score > best_score) { best = e; best_score = score; }
         }
     }
+    // the tensor-core variant exists for the register-resident batch size only
+    if (!best && allow_tc && (f & SVBASL_F_NN_TC) && m->kind == SVBASL_MODEL_ASLNN) return find_entry(m, nbt, want_eval, flavour, false);
+    if (best && (f & SVBASL_F_NN_TC) && best->nbt != nbt && allow_tc) return find_entry(m, nbt, want_eval, flavour, false);
     return best;
 }
 

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <type_traits>
 #include "voxel_step.h"
 
 namespace svb {
@@ -123,6 +124,12 @@ struct KernelEntry {
     fit_launcher_t fit;
 };
 
+// models whose run() is a CTA-cooperative routine (model_nn_tc.cuh) bracket the kernel with cta_begin / cta_end
+template <class M, class = void>
+struct is_cta_coop : std::false_type {};
+template <class M>
+struct is_cta_coop<M, std::void_t<decltype(M::kCtaCoop)>> : std::bool_constant<M::kCtaCoop> {};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -171,6 +178,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
     constexpr bool LEAN = FL != 0;
     constexpr bool SPATIAL = FL != 1;
     const bool update = LEAN || a.update;
+    if constexpr (is_cta_coop<M>::value) M::cta_begin(a.md);
     const int64_t local = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool live = local < a.e.n_vox;
     int64_t idx = live ? local : 0;
@@ -232,6 +240,9 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
         const int64_t step = step_base + it;
         const int row0 = (update && a.ad.n_batches > 1) ? (int)(step % a.ad.n_batches) : a.e.t_row0;
         float cost = vs.elbo_grad(a.md, a.e, a.ec, w, step, row0, nbt);
+        if constexpr (is_cta_coop<M>::value) {
+            if (M::cta_failed()) cost = nanf("");            // a tensor-core wait expired: no update, counted as skipped
+        }
         if (update && it == 0) cp_async_wait_all();          // only this thread reads what it copied: no barrier
         if (live) {
             if (!LEAN && a.cost) a.cost[w] = cost;
@@ -274,6 +285,7 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
         }
     }
     if (a.nan_count && skipped) atomicAdd((unsigned long long *)a.nan_count, (unsigned long long)skipped);
+    if constexpr (is_cta_coop<M>::value) M::cta_end();
     if constexpr (SPATIAL) {
         if (a.hy.done_ctas) {
             // Fused tail of the iteration: the last CTA of this launch to get here owns the hyper-parameter step.

@@ -1,0 +1,250 @@
+// model_nn_tc.cuh - the aslnn surrogate INSIDE the fused SVB step with its two 10x10 products on the 5th-generation
+// tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// AslNNModel.evaluate (/root/reference/svb_models_asl/aslnn.py:93-126, 229-260) per row (voxel, sample, time point):
+//   h1 = tanh(W0^T [t, delt] + b0),  z2 = W1^T h1 + b1,  out = W2 . tanh(z2) + b2,  signal = ftiss * out
+// and, for the gradient with respect to delttiss (forward mode, what TF autodiff yields):
+//   dz2 = W1^T ((1 - h1^2) * W0[1]),  dout = W2 . ((1 - tanh(z2)^2) * dz2).
+// The FP32-pipe kernel (model_nn.h) spends 200 of its ~410 instructions per row on the two 10x10 products plus ~50
+// uniform loads of their weights (profiles/r2_notes.md section 4).  Here one thread still owns one voxel, so the 128
+// threads of a CTA hold 128 rows at a time = one M = 128 tile:
+//   D1[128 x 16] = A1[128 x 32] . B1[32 x 16]     A1 = [hi(h1) | lo(h1) | hi(h1) | 1 1],  B1 = [Whi; Whi; Wlo; bias_hi; bias_lo]
+//   D2[128 x 16] = A2[128 x 32] . B2[32 x 16]     A2 = the same split of (1 - h1^2),      B2 from W0[1][j] W1[j][k]
+// (kind::tf32, operands split hi + lo so that the product keeps float32-level accuracy, nn_tc.cu; W and the bias arrive
+// already multiplied by 2 log2(e), so D1 feeds ftanh_c directly).  Per row: every thread writes its two A rows with
+// 16 STS.128, one CTA barrier, one elected thread issues eight K = 8 MMAs and a commit, every thread waits on the
+// mbarrier and pulls its 32 accumulator columns with one tcgen05.ld.  Four CTAs share an SM, so one CTA's tensor-core
+// round trip is covered by the others' FP32 / MUFU work.
+//
+// All waits are bounded; an expired wait raises svbasl_engine-independent status (NnTcShared::failed) that makes the
+// kernel skip its updates - a descriptor mistake must never hang the GPU.
+#pragma once
+#include "model_nn.h"
+
+namespace svb {
+
+namespace nntc {
+constexpr int kRows = 128, kN = 16, kK = 32, kChunks = kK / 4;
+constexpr uint32_t kALbo = kRows * 16, kASbo = 128, kBLbo = kN * 16, kBSbo = 128;
+constexpr int kATileFloats = kChunks * kRows * 4;        // 4096 floats = 16 KB
+constexpr int kBTileFloats = kChunks * kN * 4;           // 512 floats = 2 KB
+constexpr uint32_t kTmemCols = 32;
+// instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (2), K-major both, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+
+__host__ __device__ inline int b_index(int n, int k) {   // element (n, k) of the K-major no-swizzle B tile, in floats
+    return ((k >> 2) * (int)kBLbo + (n >> 3) * (int)kBSbo + (n & 7) * 16 + (k & 3) * 4) / 4;
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+#endif
+}  // namespace nntc
+
+#if defined(__CUDACC__)
+struct AslNNTC : AslNN {
+    static constexpr bool kCtaCoop = true;
+    static constexpr bool kRegHeavy = false;       // 4 CTAs per SM: the others cover one CTA's tensor-core round trip
+
+    struct Vox {
+        float4 *a1, *a2;              // this thread's slot in chunk 0 of the two A tiles
+        uint32_t bar, tmem, phase;    // mbarrier (shared-window address), TMEM base, parity of the next completion
+        uint64_t ad1, ad2, bd1, bd2;  // shared-memory matrix descriptors
+        int *failed;
+    };
+
+    struct Shared {
+        alignas(1024) float a1[nntc::kATileFloats];
+        alignas(1024) float a2[nntc::kATileFloats];
+        alignas(128) float b1[nntc::kBTileFloats];
+        alignas(128) float b2[nntc::kBTileFloats];
+        alignas(8) uint64_t bar;
+        uint32_t tmem_base;
+        int failed;
+        uint32_t phase[nntc::kRows];  // per thread: parity of the next mbarrier completion (survives load_vox)
+    };
+
+    static __device__ __forceinline__ Shared &shared() {
+        __shared__ Shared sh;
+        return sh;
+    }
+
+    // once per CTA: weight tiles (hi / lo split, bias rows), mbarrier, TMEM columns
+    static __device__ void cta_begin(const DevModel &m) {
+        Shared &sh = shared();
+        const NNWeights &w = m.nn;
+        const int tid = threadIdx.x;
+        for (int i = tid; i < nntc::kBTileFloats; i += blockDim.x) { sh.b1[i] = 0.0f; sh.b2[i] = 0.0f; }
+        __syncthreads();
+        for (int i = tid; i < H * H; i += blockDim.x) {
+            const int n = i / H, j = i - n * H;                    // n = output unit k, j = input unit
+            const float v1 = w.w1_c[n][j], v2 = w.w1d[n][j];
+            const float h1 = nntc::tf32_hi(v1), h2 = nntc::tf32_hi(v2);
+            sh.b1[nntc::b_index(n, j)] = h1;
+            sh.b1[nntc::b_index(n, H + j)] = h1;
+            sh.b1[nntc::b_index(n, 2 * H + j)] = v1 - h1;
+            sh.b2[nntc::b_index(n, j)] = h2;
+            sh.b2[nntc::b_index(n, H + j)] = h2;
+            sh.b2[nntc::b_index(n, 2 * H + j)] = v2 - h2;
+        }
+        if (tid < H) {                                             // bias rows: A1 carries 1.0 in K = 30, 31
+            const float b = w.b1_c[tid], bh = nntc::tf32_hi(b);
+            sh.b1[nntc::b_index(tid, 30)] = bh;
+            sh.b1[nntc::b_index(tid, 31)] = b - bh;
+        }
+        sh.phase[tid & (nntc::kRows - 1)] = 0u;
+        if (tid == 0) {
+            sh.failed = 0;
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(nntc::smem_u32(&sh.bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if ((tid >> 5) == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(nntc::smem_u32(&sh.tmem_base)), "r"(nntc::kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // B tiles: generic-proxy writes -> async proxy
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+
+    static __device__ void cta_end() {
+        Shared &sh = shared();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if ((threadIdx.x >> 5) == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sh.tmem_base), "r"(nntc::kTmemCols));
+    }
+    static __device__ bool cta_failed() { return shared().failed != 0; }
+
+    template <class Acc>
+    static __device__ __forceinline__ void bind_times(const DevModel &, Vox &, const Acc &) {}
+
+    static __device__ __forceinline__ Vox load_vox(const DevModel &, int64_t) {
+        Shared &sh = shared();
+        Vox v;
+        const int tid = threadIdx.x;
+        v.a1 = reinterpret_cast<float4 *>(sh.a1) + (tid >> 3) * (nntc::kASbo / 16) + (tid & 7);
+        v.a2 = reinterpret_cast<float4 *>(sh.a2) + (tid >> 3) * (nntc::kASbo / 16) + (tid & 7);
+        v.bar = nntc::smem_u32(&sh.bar);
+        v.tmem = sh.tmem_base;
+        v.phase = sh.phase[tid];
+        v.ad1 = nntc::umma_desc(nntc::smem_u32(sh.a1), nntc::kALbo, nntc::kASbo);
+        v.ad2 = nntc::umma_desc(nntc::smem_u32(sh.a2), nntc::kALbo, nntc::kASbo);
+        v.bd1 = nntc::umma_desc(nntc::smem_u32(sh.b1), nntc::kBLbo, nntc::kBSbo);
+        v.bd2 = nntc::umma_desc(nntc::smem_u32(sh.b2), nntc::kBLbo, nntc::kBSbo);
+        v.failed = &sh.failed;
+        return v;
+    }
+
+    // one A row: [hi(10) | lo(10) | hi(10) | tail0 tail1] as eight 16-byte chunks (conflict free: a core matrix is
+    // 8 rows x 16 B, consecutive rows are consecutive 16-byte words)
+    static __device__ __forceinline__ void store_row(float4 *dst, const float *x, float tail) {
+        float r[nntc::kK];
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const float hi = nntc::tf32_hi(x[j]);
+            r[j] = hi;
+            r[H + j] = x[j] - hi;
+            r[2 * H + j] = hi;
+        }
+        r[30] = tail;
+        r[31] = tail;
+#pragma unroll
+        for (int c = 0; c < nntc::kChunks; ++c)
+            dst[c * (nntc::kALbo / 16)] = make_float4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+    }
+
+    static __device__ __forceinline__ bool wait_bounded(uint32_t bar, uint32_t parity) {
+        for (int spin = 0; spin < (1 << 22); ++spin) {
+            uint32_t ok;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            if (ok) return true;
+        }
+        return false;
+    }
+
+    // Every thread of the CTA calls this together (the sample and time-point loops are uniform).
+    template <class Acc>
+    static __device__ __forceinline__ void run(const DevModel &m, Vox &v, const float *x, Acc &acc) {
+        const NNWeights &w = m.nn;
+        const Sample s = AslNN::prep_sample(m, AslNN::Vox(), x);
+        const int nb = Acc::NB > 0 ? Acc::NB : acc.n();
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            const float t = acc.time(b);
+            float h1[H], g1[H];
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                const float h = ftanh_c(w.w0t_c[j] * t + s.a1[j]);
+                h1[j] = h;
+                g1[j] = 1.0f - h * h;
+            }
+            store_row(v.a1, h1, 1.0f);
+            store_row(v.a2, g1, 0.0f);
+            // generic-proxy writes -> visible to the tensor core's async proxy, then hand over to the issuing thread
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const uint64_t ad0 = half ? v.ad2 : v.ad1, bd0 = half ? v.bd2 : v.bd1;
+                    const uint32_t d = v.tmem + (uint32_t)(half * nntc::kN);
+#pragma unroll
+                    for (int ks = 0; ks < nntc::kK / 8; ++ks) {
+                        // each K = 8 slice spans two 16-byte chunks: advance the start address by 2*LBO (16-B units)
+                        const uint64_t ad = ad0 + (uint64_t)((2 * ks * nntc::kALbo) >> 4);
+                        const uint64_t bd = bd0 + (uint64_t)((2 * ks * nntc::kBLbo) >> 4);
+                        const uint32_t accum = ks > 0 ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(d), "l"(ad), "l"(bd), "r"(nntc::kIdesc), "r"(accum) : "memory");
+                    }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(v.bar) : "memory");
+            }
+            if (*(volatile int *)v.failed == 0 && !wait_bounded(v.bar, v.phase)) atomicExch(v.failed, 1);
+            v.phase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t r[32];
+            const uint32_t taddr = v.tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // (the next row's barrier orders these reads before the MMAs that overwrite D and the stores that overwrite A)
+            float out = w.b2, dout = 0.0f;
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const float h = ftanh_c(__uint_as_float(r[k]));               // D1 = 2 log2(e) (W1^T h1 + b1)
+                out += w.w2[k] * h;
+                dout += (w.w2[k] * __uint_as_float(r[nntc::kN + k])) * (1.0f - h * h);
+            }
+            float d[PA];
+            d[0] = out;
+            d[1] = s.f * dout;
+            acc.add(b, s.f * out, d);
+        }
+        shared().phase[threadIdx.x] = v.phase;
+    }
+};
+#endif
+
+}  // namespace svb

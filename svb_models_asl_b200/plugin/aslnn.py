@@ -108,6 +108,8 @@ class AslNNModel(Model):
         m = L.Model()
         m.kind = self.KIND
         m.flags = L.F_CASL if self.casl else 0
+        if getattr(self, "use_tensor_cores", False):
+            m.flags |= L.F_NN_TC             # fused step: the two 10x10 products on tcgen05 (csrc/model_nn_tc.cuh)
         m.tau, m.t1b = self.tau, self.t1b
         packed = self.packed_weights()
         m.nn_weights = packed.ctypes.data                                # HOST pointer, copied into kernel args

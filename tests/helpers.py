@@ -98,6 +98,8 @@ class Backend:
             assert packed.size == 151
             self.keep.append(packed)
             m.nn_weights = packed.ctypes.data
+            if cfg.get("tensor_cores"):
+                m.flags = L.F_NN_TC
             return m
         m.kind = L.MODEL_ASLREST_DISP if cfg.disp else L.MODEL_ASLREST
         m.flags = cfg_flags(cfg)

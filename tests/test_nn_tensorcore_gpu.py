@@ -64,3 +64,60 @@ def test_tensor_core_sass_is_blackwell_native():
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP"):
         assert mnemonic in sass, mnemonic
+
+
+def _nn_problem(golden, W, rng):
+    import torch
+    from oracle import asl_models as om
+    n = golden("aslnn_eval")["nn"]
+    ws, bs = [n["w%i" % i] for i in range(3)], [n["b%i" % i] for i in range(3)]
+    spec = H.nn_spec(ws, bs, latent="numeric")
+    tpts = np.repeat(np.asarray(H.TIS, dtype=np.float32)[:, None], W, 1)
+    state = np.stack([rng.normal(1.5, 0.5, W), rng.normal(1.2, 0.6, W) * rng.choice([-1, 1], W), rng.normal(0, 0.3, W)]
+                     + [rng.normal(-2, 0.5, W) for _ in range(3)] + [rng.normal(0, 0.05, W) for _ in range(3)])
+    state = state.astype(np.float32).astype(np.float64)
+    f = torch.as_tensor(np.exp(state[0])).reshape(W, 1, 1)
+    d = torch.as_tensor(np.abs(state[1])).reshape(W, 1, 1)
+    clean = om.evaluate_nn(ws, bs, f, d, torch.as_tensor(tpts.astype(np.float64)).T.unsqueeze(1))[:, 0, :].T.numpy()
+    prob = {"state": state, "tpts": tpts, "data": (clean + rng.normal(0, 0.5, clean.shape)).astype(np.float32)}
+    return spec, prob
+
+
+def test_fused_step_with_tensor_core_products_matches_oracle(golden, record_error):
+    """The fused ELBO + gradient of aslnn with the two 10x10 products per row on tcgen05 (csrc/model_nn_tc.cuh;
+    SVBASL_F_NN_TC): cost and gradient against the oracle (autograd through the MLP, aslnn.py:238-260) at the north-star
+    tolerances, on 300 voxels = two full 128-row tiles and a ragged one."""
+    from tests.test_kernel_parity import _check_grads, _record_grad_errors
+    be = H.Backend("cuda")
+    rng = np.random.default_rng(44)
+    W = 300
+    spec, prob = _nn_problem(golden, W, rng)
+    eps = rng.normal(size=(3, spec.n_samples, W)).astype(np.float32)
+    ocost, ograd, _gh, _ = H.oracle_cost_grad(spec, prob, eps)
+    m = be.model_desc(dict(spec.cfg, tensor_cores=True))
+    e, _b = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], eps)
+    cost, grad, _ = be.elbo_grad(m, e, spec.n_state)
+    _record_grad_errors(record_error, "nn_tc_fused/cuda", cost, grad, ocost, ograd)
+    _check_grads(cost, grad, ocost, ograd)
+
+
+def test_production_step_tensor_cores_equals_fp32_pipe(golden):
+    """svbasl_step (lean flavour, in-kernel draws, 3 fused iterations per launch) with and without SVBASL_F_NN_TC:
+    same posterior after 6 iterations up to float32 rounding of the two product forms."""
+    be = H.Backend("cuda")
+    rng = np.random.default_rng(45)
+    W = 1000
+    spec, prob = _nn_problem(golden, W, rng)
+    finals = []
+    for tc in (False, True):
+        m = be.model_desc(dict(spec.cfg, tensor_cores=tc))
+        e, bufs = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], None, seed=9)
+        ad, _ab = be.adam_desc(spec.n_state, W, 0.05, 8, n_iters=3)
+        for launch in range(2):
+            ad.step0 = 3 * launch
+            csum, nanc = be.step(m, e, ad)
+            assert nanc == 0 and np.isfinite(csum).all()
+        finals.append(be.get(bufs["state"]))
+    assert np.abs(finals[0] - prob["state"]).max() > 0.05
+    stats = H.trajectory_error(finals[1], finals[0])
+    assert stats["q50"] <= 2e-6 and stats["q99"] <= 1e-4 and stats["max_abs"] <= 0.05, stats
