@@ -28,7 +28,7 @@ constexpr int kRows = 128, kN = 16, kK = 32, kChunks = kK / 4;
 constexpr uint32_t kALbo = kRows * 16, kASbo = 128, kBLbo = kN * 16, kBSbo = 128;
 constexpr int kATileFloats = kChunks * kRows * 4;        // 4096 floats = 16 KB
 constexpr int kBTileFloats = kChunks * kN * 4;           // 512 floats = 2 KB
-constexpr uint32_t kTmemCols = 32;
+constexpr uint32_t kTmemCols = 64;                    // two accumulator pairs (D1 | D2) of 16 columns each
 // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (2), K-major both, N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
 
@@ -172,54 +172,69 @@ struct AslNNTC : AslNN {
         return false;
     }
 
+    static __device__ __forceinline__ void layer1(const NNWeights &w, const Sample &s, float t, float *h1, float *g1) {
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const float h = ftanh_c(w.w0t_c[j] * t + s.a1[j]);
+            h1[j] = h;
+            g1[j] = 1.0f - h * h;
+        }
+    }
+
+    // A rows of this thread -> shared memory, CTA barrier, eight MMAs into accumulator pair `buf`, commit
+    static __device__ __forceinline__ void issue(const Vox &v, const float *h1, const float *g1, int buf) {
+        store_row(v.a1, h1, 1.0f);
+        store_row(v.a2, g1, 0.0f);
+        // generic-proxy writes -> visible to the tensor core's async proxy, then hand over to the issuing thread
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint64_t ad0 = half ? v.ad2 : v.ad1, bd0 = half ? v.bd2 : v.bd1;
+                const uint32_t d = v.tmem + (uint32_t)(buf * 2 * nntc::kN + half * nntc::kN);
+#pragma unroll
+                for (int ks = 0; ks < nntc::kK / 8; ++ks) {
+                    // each K = 8 slice spans two 16-byte chunks: advance the start address by 2*LBO (16-B units)
+                    const uint64_t ad = ad0 + (uint64_t)((2 * ks * nntc::kALbo) >> 4);
+                    const uint64_t bd = bd0 + (uint64_t)((2 * ks * nntc::kBLbo) >> 4);
+                    const uint32_t accum = ks > 0 ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "setp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(d), "l"(ad), "l"(bd), "r"(nntc::kIdesc), "r"(accum) : "memory");
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(v.bar) : "memory");
+        }
+    }
+
     // Every thread of the CTA calls this together (the sample and time-point loops are uniform).
+    // Software pipeline over the time points of one sample: while the tensor core works on row b+1, the threads read
+    // row b's accumulators, run layer 2 and the output layer for it and layer 1 of row b+2.  One A-tile pair (the wait
+    // for row b's MMAs also frees it), two accumulator pairs in TMEM, one mbarrier (at most one commit outstanding when
+    // it is waited on).
     template <class Acc>
     static __device__ __forceinline__ void run(const DevModel &m, Vox &v, const float *x, Acc &acc) {
         const NNWeights &w = m.nn;
         const Sample s = AslNN::prep_sample(m, AslNN::Vox(), x);
         const int nb = Acc::NB > 0 ? Acc::NB : acc.n();
+        float h1[H], g1[H];
+        layer1(w, s, acc.time(0), h1, g1);
+        issue(v, h1, g1, 0);
 #pragma unroll 1
         for (int b = 0; b < nb; ++b) {
-            const float t = acc.time(b);
-            float h1[H], g1[H];
-#pragma unroll
-            for (int j = 0; j < H; ++j) {
-                const float h = ftanh_c(w.w0t_c[j] * t + s.a1[j]);
-                h1[j] = h;
-                g1[j] = 1.0f - h * h;
-            }
-            store_row(v.a1, h1, 1.0f);
-            store_row(v.a2, g1, 0.0f);
-            // generic-proxy writes -> visible to the tensor core's async proxy, then hand over to the issuing thread
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const uint64_t ad0 = half ? v.ad2 : v.ad1, bd0 = half ? v.bd2 : v.bd1;
-                    const uint32_t d = v.tmem + (uint32_t)(half * nntc::kN);
-#pragma unroll
-                    for (int ks = 0; ks < nntc::kK / 8; ++ks) {
-                        // each K = 8 slice spans two 16-byte chunks: advance the start address by 2*LBO (16-B units)
-                        const uint64_t ad = ad0 + (uint64_t)((2 * ks * nntc::kALbo) >> 4);
-                        const uint64_t bd = bd0 + (uint64_t)((2 * ks * nntc::kBLbo) >> 4);
-                        const uint32_t accum = ks > 0 ? 1u : 0u;
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\t"
-                            "setp.ne.b32 p, %4, 0;\n\t"
-                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                            ::"r"(d), "l"(ad), "l"(bd), "r"(nntc::kIdesc), "r"(accum) : "memory");
-                    }
-                }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(v.bar) : "memory");
-            }
+            const bool more = b + 1 < nb;
+            if (more) layer1(w, s, acc.time(b + 1), h1, g1);
             if (*(volatile int *)v.failed == 0 && !wait_bounded(v.bar, v.phase)) atomicExch(v.failed, 1);
             v.phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (more) issue(v, h1, g1, (b + 1) & 1);
             uint32_t r[32];
-            const uint32_t taddr = v.tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
+            const uint32_t taddr = v.tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16) + (uint32_t)((b & 1) * 2 * nntc::kN);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -229,7 +244,8 @@ struct AslNNTC : AslNN {
                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            // (the next row's barrier orders these reads before the MMAs that overwrite D and the stores that overwrite A)
+            // (accumulator pair b&1 is overwritten by row b+2's MMAs, issued behind the next CTA barrier: every thread
+            // has finished this load by then)
             float out = w.b2, dout = 0.0f;
 #pragma unroll
             for (int k = 0; k < H; ++k) {

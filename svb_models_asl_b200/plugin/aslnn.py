@@ -21,6 +21,10 @@ from .aslrest import AslRestModel, __version__
 LAYERS = [(2, 10), (10, 10), (10, 1)]           # aslnn.py:238-240
 
 
+# fused step on tcgen05 by default?  (measured: profiles/r2_notes.md section 4)
+TENSOR_CORE_STEP_DEFAULT = False
+
+
 class AslNNModel(Model):
     """ASL resting state model using NN for evaluation"""
 
@@ -46,6 +50,10 @@ class AslNNModel(Model):
         ModelOption("train_examples", "Number of training examples", type=int, default=500),
         ModelOption("train_save", "Directory to save trained model weights to"),
         ModelOption("train_load", "Directory to load trained model weights from"),
+        # extensions of this engine (no counterpart in the reference): where the 10x10 layer runs
+        ModelOption("use_tensor_cores", "evaluate(): 10x10 layer on the tensor cores (csrc/nn_tc.cu)", type=bool, default=False),
+        ModelOption("tensor_core_step", "fused SVB step: the two 10x10 products per row on the tensor cores "
+                    "(csrc/model_nn_tc.cuh)", type=bool, default=TENSOR_CORE_STEP_DEFAULT),
     ]
 
     KIND = L.MODEL_ASLNN
@@ -108,7 +116,7 @@ class AslNNModel(Model):
         m = L.Model()
         m.kind = self.KIND
         m.flags = L.F_CASL if self.casl else 0
-        if getattr(self, "use_tensor_cores", False):
+        if getattr(self, "tensor_core_step", False):
             m.flags |= L.F_NN_TC             # fused step: the two 10x10 products on tcgen05 (csrc/model_nn_tc.cuh)
         m.tau, m.t1b = self.tau, self.t1b
         packed = self.packed_weights()

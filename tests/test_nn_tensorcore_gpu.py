@@ -7,6 +7,8 @@ import numpy as np
 import pytest
 import torch
 
+from tests import helpers as H
+
 pytestmark = pytest.mark.gpu
 
 
