@@ -11,10 +11,16 @@
 //   D1[128 x 16] = A1[128 x 32] . B1[32 x 16]     A1 = [hi(h1) | lo(h1) | hi(h1) | 1 1],  B1 = [Whi; Whi; Wlo; bias_hi; bias_lo]
 //   D2[128 x 16] = A2[128 x 32] . B2[32 x 16]     A2 = the same split of (1 - h1^2),      B2 from W0[1][j] W1[j][k]
 // (kind::tf32, operands split hi + lo so that the product keeps float32-level accuracy, nn_tc.cu; W and the bias arrive
-// already multiplied by 2 log2(e), so D1 feeds ftanh_c directly).  Per row: every thread writes its two A rows with
-// 16 STS.128, one CTA barrier, one elected thread issues eight K = 8 MMAs and a commit, every thread waits on the
-// mbarrier and pulls its 32 accumulator columns with one tcgen05.ld.  Four CTAs share an SM, so one CTA's tensor-core
-// round trip is covered by the others' FP32 / MUFU work.
+// already multiplied by 2 log2(e), so D1 feeds ftanh_c directly).
+//
+// The A operands live in TENSOR MEMORY, not in shared memory: row i of an M = 128 operand is TMEM lane i, so a thread
+// writes its own two A rows with two tcgen05.st (32 columns each) straight from registers.  (The first version staged A
+// in shared memory: 16 STS.128 per thread and row plus the tensor core's reads of the same 32 KB made the shared-memory
+// pipe the limiter - profiles/r2_notes.md section 4.)  Only the two 2 KB weight tiles B1, B2 sit in shared memory.
+// Per row: two tcgen05.st, one CTA barrier, one thread (the duty rotates over the warps) issues eight K = 8 MMAs and a
+// commit, every thread waits on the mbarrier and pulls its 32 accumulator columns with one tcgen05.ld.  TMEM columns per CTA: A1 32 | A2 32 |
+// two accumulator pairs 2 x 32 = 128, so four CTAs share an SM's 512 columns and one CTA's tensor-core round trip is
+// covered by the others' FP32 / MUFU work.
 //
 // All waits are bounded; an expired wait raises svbasl_engine-independent status (NnTcShared::failed) that makes the
 // kernel skip its updates - a descriptor mistake must never hang the GPU.
@@ -25,10 +31,10 @@ namespace svb {
 
 namespace nntc {
 constexpr int kRows = 128, kN = 16, kK = 32, kChunks = kK / 4;
-constexpr uint32_t kALbo = kRows * 16, kASbo = 128, kBLbo = kN * 16, kBSbo = 128;
-constexpr int kATileFloats = kChunks * kRows * 4;        // 4096 floats = 16 KB
+constexpr uint32_t kBLbo = kN * 16, kBSbo = 128;
 constexpr int kBTileFloats = kChunks * kN * 4;           // 512 floats = 2 KB
-constexpr uint32_t kTmemCols = 64;                    // two accumulator pairs (D1 | D2) of 16 columns each
+constexpr uint32_t kTmemCols = 128;                   // A1 (32) | A2 (32) | two accumulator pairs (D1 | D2), 32 each
+constexpr uint32_t kColA1 = 0, kColA2 = kK, kColD = 2 * kK;
 // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (2), K-major both, N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
 
@@ -51,15 +57,13 @@ struct AslNNTC : AslNN {
     static constexpr bool kRegHeavy = false;       // 4 CTAs per SM: the others cover one CTA's tensor-core round trip
 
     struct Vox {
-        float4 *a1, *a2;              // this thread's slot in chunk 0 of the two A tiles
-        uint32_t bar, tmem, phase;    // mbarrier (shared-window address), TMEM base, parity of the next completion
-        uint64_t ad1, ad2, bd1, bd2;  // shared-memory matrix descriptors
+        uint32_t bar, tmem, phase;    // mbarrier (shared-window address), TMEM base, (rows issued << 1) | parity of the next completion
+        uint32_t tlane;               // TMEM address of this warp's 32 lanes, column 0 of the allocation
+        uint64_t bd1, bd2;            // shared-memory matrix descriptors of the weight tiles
         int *failed;
     };
 
     struct Shared {
-        alignas(1024) float a1[nntc::kATileFloats];
-        alignas(1024) float a2[nntc::kATileFloats];
         alignas(128) float b1[nntc::kBTileFloats];
         alignas(128) float b2[nntc::kBTileFloats];
         alignas(8) uint64_t bar;
@@ -82,7 +86,7 @@ struct AslNNTC : AslNN {
         __syncthreads();
         for (int i = tid; i < H * H; i += blockDim.x) {
             const int n = i / H, j = i - n * H;                    // n = output unit k, j = input unit
-            const float v1 = w.w1_c[n][j], v2 = w.w1d[n][j];
+            const float v1 = w.w1_c[n][j], v2 = w.w1d[n][j] * w.w2[n];       // D2 arrives multiplied by the output weight
             const float h1 = nntc::tf32_hi(v1), h2 = nntc::tf32_hi(v2);
             sh.b1[nntc::b_index(n, j)] = h1;
             sh.b1[nntc::b_index(n, H + j)] = h1;
@@ -128,47 +132,54 @@ struct AslNNTC : AslNN {
         Shared &sh = shared();
         Vox v;
         const int tid = threadIdx.x;
-        v.a1 = reinterpret_cast<float4 *>(sh.a1) + (tid >> 3) * (nntc::kASbo / 16) + (tid & 7);
-        v.a2 = reinterpret_cast<float4 *>(sh.a2) + (tid >> 3) * (nntc::kASbo / 16) + (tid & 7);
         v.bar = nntc::smem_u32(&sh.bar);
         v.tmem = sh.tmem_base;
+        v.tlane = sh.tmem_base + ((uint32_t)((tid >> 5) * 32) << 16);
         v.phase = sh.phase[tid];
-        v.ad1 = nntc::umma_desc(nntc::smem_u32(sh.a1), nntc::kALbo, nntc::kASbo);
-        v.ad2 = nntc::umma_desc(nntc::smem_u32(sh.a2), nntc::kALbo, nntc::kASbo);
         v.bd1 = nntc::umma_desc(nntc::smem_u32(sh.b1), nntc::kBLbo, nntc::kBSbo);
         v.bd2 = nntc::umma_desc(nntc::smem_u32(sh.b2), nntc::kBLbo, nntc::kBSbo);
         v.failed = &sh.failed;
         return v;
     }
 
-    // one A row: [hi(10) | lo(10) | hi(10) | tail0 tail1] as eight 16-byte chunks (conflict free: a core matrix is
-    // 8 rows x 16 B, consecutive rows are consecutive 16-byte words)
-    static __device__ __forceinline__ void store_row(float4 *dst, const float *x, float tail) {
-        float r[nntc::kK];
+    // one A row: [hi(10) | lo(10) | hi(10) | tail0 tail1] -> this thread's TMEM lane, 32 columns from `taddr`
+    static __device__ __forceinline__ void store_row(uint32_t taddr, const float *x, float tail) {
+        uint32_t r[nntc::kK];
 #pragma unroll
         for (int j = 0; j < H; ++j) {
             const float hi = nntc::tf32_hi(x[j]);
-            r[j] = hi;
-            r[H + j] = x[j] - hi;
-            r[2 * H + j] = hi;
+            r[j] = __float_as_uint(hi);
+            r[H + j] = __float_as_uint(x[j] - hi);
+            r[2 * H + j] = __float_as_uint(hi);
         }
-        r[30] = tail;
-        r[31] = tail;
-#pragma unroll
-        for (int c = 0; c < nntc::kChunks; ++c)
-            dst[c * (nntc::kALbo / 16)] = make_float4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+        r[30] = __float_as_uint(tail);
+        r[31] = __float_as_uint(tail);
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+            "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+            ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+              "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+              "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+              "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+            : "memory");
     }
 
-    static __device__ __forceinline__ bool wait_bounded(uint32_t bar, uint32_t parity) {
+    static __device__ __forceinline__ bool try_wait(uint32_t bar, uint32_t parity) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        return ok != 0;
+    }
+    // bounded: gives up when another thread of the CTA has, or after ~4 M polls of its own
+    static __device__ __noinline__ bool wait_slow(uint32_t bar, uint32_t parity, int *failed) {
         for (int spin = 0; spin < (1 << 22); ++spin) {
-            uint32_t ok;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-            if (ok) return true;
+            if (try_wait(bar, parity)) return true;
+            if (*(volatile int *)failed != 0) return false;
         }
+        atomicExch(failed, 1);
         return false;
     }
 
@@ -181,31 +192,37 @@ struct AslNNTC : AslNN {
         }
     }
 
-    // A rows of this thread -> shared memory, CTA barrier, eight MMAs into accumulator pair `buf`, commit
-    static __device__ __forceinline__ void issue(const Vox &v, const float *h1, const float *g1, int buf) {
-        store_row(v.a1, h1, 1.0f);
-        store_row(v.a2, g1, 0.0f);
-        // generic-proxy writes -> visible to the tensor core's async proxy, then hand over to the issuing thread
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // A rows of this thread -> tensor memory, CTA barrier, eight MMAs into accumulator pair `buf`, commit
+    static __device__ __forceinline__ void issue(Vox &v, const float *h1, const float *g1, int buf) {
+        store_row(v.tlane + nntc::kColA1, h1, 1.0f);
+        store_row(v.tlane + nntc::kColA2, g1, 0.0f);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");      // the rows are in TMEM: hand over to the issuer
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (threadIdx.x == 0) {
+        // the issuing duty goes round the four warps (= the SM's four schedulers) row by row: a fixed issuer would load
+        // one scheduler with every resident CTA's issue work.  (Tried instead of the barrier: the warps count themselves
+        // in with a shared-memory atomic and the last one issues - 0.96 G against 1.07 G voxel-iters/s, the slowest warp
+        // gets the issue work on top and the others spin on the mbarrier instead of sleeping at the barrier.)
+        const uint32_t issuer = ((v.phase >> 1) & 3u) << 5;
+        v.phase += 2u;
+        if (threadIdx.x == issuer) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const uint64_t ad0 = half ? v.ad2 : v.ad1, bd0 = half ? v.bd2 : v.bd1;
-                const uint32_t d = v.tmem + (uint32_t)(buf * 2 * nntc::kN + half * nntc::kN);
+                const uint64_t bd0 = half ? v.bd2 : v.bd1;
+                const uint32_t a0 = v.tmem + (half ? nntc::kColA2 : nntc::kColA1);
+                const uint32_t d = v.tmem + nntc::kColD + (uint32_t)(buf * 2 * nntc::kN + half * nntc::kN);
 #pragma unroll
                 for (int ks = 0; ks < nntc::kK / 8; ++ks) {
-                    // each K = 8 slice spans two 16-byte chunks: advance the start address by 2*LBO (16-B units)
-                    const uint64_t ad = ad0 + (uint64_t)((2 * ks * nntc::kALbo) >> 4);
+                    // a K = 8 slice of A is 8 TMEM columns; of B two 16-byte chunks: start address + 2*LBO (16-B units)
+                    const uint32_t at = a0 + (uint32_t)(8 * ks);
                     const uint64_t bd = bd0 + (uint64_t)((2 * ks * nntc::kBLbo) >> 4);
                     const uint32_t accum = ks > 0 ? 1u : 0u;
                     asm volatile(
                         "{\n\t.reg .pred p;\n\t"
                         "setp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                        ::"r"(d), "l"(ad), "l"(bd), "r"(nntc::kIdesc), "r"(accum) : "memory");
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                        ::"r"(d), "r"(at), "l"(bd), "r"(nntc::kIdesc), "r"(accum) : "memory");
                 }
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(v.bar) : "memory");
@@ -214,7 +231,7 @@ struct AslNNTC : AslNN {
 
     // Every thread of the CTA calls this together (the sample and time-point loops are uniform).
     // Software pipeline over the time points of one sample: while the tensor core works on row b+1, the threads read
-    // row b's accumulators, run layer 2 and the output layer for it and layer 1 of row b+2.  One A-tile pair (the wait
+    // row b's accumulators, run layer 2 and the output layer for it and layer 1 of row b+2.  One A pair in TMEM (the wait
     // for row b's MMAs also frees it), two accumulator pairs in TMEM, one mbarrier (at most one commit outstanding when
     // it is waited on).
     template <class Acc>
@@ -229,12 +246,12 @@ struct AslNNTC : AslNN {
         for (int b = 0; b < nb; ++b) {
             const bool more = b + 1 < nb;
             if (more) layer1(w, s, acc.time(b + 1), h1, g1);
-            if (*(volatile int *)v.failed == 0 && !wait_bounded(v.bar, v.phase)) atomicExch(v.failed, 1);
+            if (!try_wait(v.bar, v.phase & 1u)) wait_slow(v.bar, v.phase & 1u, v.failed);
             v.phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (more) issue(v, h1, g1, (b + 1) & 1);
             uint32_t r[32];
-            const uint32_t taddr = v.tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16) + (uint32_t)((b & 1) * 2 * nntc::kN);
+            const uint32_t taddr = v.tlane + nntc::kColD + (uint32_t)((b & 1) * 2 * nntc::kN);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -251,7 +268,7 @@ struct AslNNTC : AslNN {
             for (int k = 0; k < H; ++k) {
                 const float h = ftanh_c(__uint_as_float(r[k]));               // D1 = 2 log2(e) (W1^T h1 + b1)
                 out += w.w2[k] * h;
-                dout += (w.w2[k] * __uint_as_float(r[nntc::kN + k])) * (1.0f - h * h);
+                dout += __uint_as_float(r[nntc::kN + k]) * (1.0f - h * h);      // D2 = W2[k] * dz2[k]
             }
             float d[PA];
             d[0] = out;
