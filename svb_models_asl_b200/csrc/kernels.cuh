@@ -236,10 +236,20 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
     int skipped = 0;
     const int64_t step_base = a.e.step_dev ? (int64_t)*a.e.step_dev : a.step;   // device counter under graph replay
     double *cost_sum = a.cost_sum ? a.cost_sum + ((a.e.step_dev && !a.e.cost_sum_scalar) ? step_base : 0) : nullptr;
+    // the batch (data, time points, what the model derives from them) is loaded when its row changes: once per launch
+    // when all fused iterations see the same batch
+    typename M::Vox vox = M::load_vox(a.md, w);
+    BatchAcc<VS::P, NBT> acc;
+    int row_loaded = -1;
     for (int it = 0; it < n_iters; ++it) {
         const int64_t step = step_base + it;
         const int row0 = (update && a.ad.n_batches > 1) ? (int)(step % a.ad.n_batches) : a.e.t_row0;
-        float cost = vs.elbo_grad(a.md, a.e, a.ec, w, step, row0, nbt);
+        if (row0 != row_loaded) {
+            acc.load(a.e, w, row0);
+            M::bind_times(a.md, vox, acc);
+            row_loaded = row0;
+        }
+        float cost = vs.elbo_grad_batch(a.md, a.e, a.ec, w, step, vox, acc, nbt);
         if constexpr (is_cta_coop<M>::value) {
             if (M::cta_failed()) cost = nanf("");            // a tensor-core wait expired: no update, counted as skipped
         }

@@ -264,6 +264,17 @@ struct VoxelStep {
     // Cost of this voxel for one batch, gradients left in g_*.  Returns the un-scaled cost.
     SVB_HD float elbo_grad(const DevModel &md, const svbasl_engine &e, const EngineConst &ec, int64_t w, int64_t step,
                            int row0, const NbTile nbt = NbTile{nullptr, 0, -1, 0u}) {
+        typename M::Vox vox = M::load_vox(md, w);
+        BatchAcc<P, NBT> acc;
+        acc.load(e, w, row0);
+        M::bind_times(md, vox, acc);
+        return elbo_grad_batch(md, e, ec, w, step, vox, acc, nbt);
+    }
+
+    // The same with the batch (data, time points, per-time-point model constants) already loaded: the iterations fused
+    // into one launch share it when every iteration sees the same batch (n_batches == 1).
+    SVB_HD float elbo_grad_batch(const DevModel &md, const svbasl_engine &e, const EngineConst &ec, int64_t w, int64_t step,
+                                 typename M::Vox &vox, BatchAcc<P, NBT> &acc, const NbTile nbt = NbTile{nullptr, 0, -1, 0u}) {
         const int S = e.n_samples;
         const float Tf = ec.t_full;
         const float scale = ec.scale;
@@ -271,10 +282,6 @@ struct VoxelStep {
         const bool numeric = LEAN || (e.latent == SVBASL_LATENT_NUMERIC);
         const bool eps_mem = !LEAN && e.eps != nullptr;
         const uint32_t key = rng_key(e.seed, step);
-        typename M::Vox vox = M::load_vox(md, w);
-        BatchAcc<P, NBT> acc;
-        acc.load(e, w, row0);
-        M::bind_times(md, vox, acc);
 
         Terms tm;
         prior_terms(e, ec, tm);
