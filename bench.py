@@ -70,7 +70,8 @@ WORKLOADS = {
                  batch=6, repeats=8, voxels=250_000,
                  desc="aslrest_disp gamma dispersion, 6 PLD x 8 repeats, ftiss+delttiss+arterial+s+sp, S=10, T=48, B=6"),
     "nn": dict(model="aslnn", options={"tau": 1.8, "casl": True, "plds": PLDS, "repeats": [1]}, batch=None, repeats=1,
-               voxels=1_000_000, desc="aslnn MLP surrogate 2-10-10-1, ftiss+delttiss, S=10, B=T=6"),
+               voxels=1_000_000, desc="aslnn MLP surrogate 2-10-10-1 (plugin defaults: 10x10 products of the fused step on tcgen05), "
+                                      "ftiss+delttiss, S=10, B=T=6"),
     "nn_tc": dict(model="aslnn", options={"tau": 1.8, "casl": True, "plds": PLDS, "repeats": [1], "tensor_core_step": True},
                   batch=None, repeats=1, voxels=1_000_000,
                   desc="aslnn MLP surrogate 2-10-10-1 with the 10x10 products of the fused step on tcgen05, S=10, B=T=6"),
@@ -83,8 +84,10 @@ WORKLOADS = {
                     desc="aslrest with spatial MRF prior on ftiss, 6 PLD x 8 repeats, S=10, T=48, B=6, 100^3 volume"),
 }
 # algorithmic FP32 lane-instructions and MUFU (XU-pipe) operations per voxel-iteration
-LANE_INSTR = {"nn_tc": 60 * 420 + 10 * 30 + 200, "nn_fp32": 60 * 420 + 10 * 30 + 200, "sim_art": 60 * 50 + 10 * 60 + 300, "real_like": 60 * 21 + 10 * 30 + 200, "spatial": 60 * 21 + 10 * 30 + 200,
-              "nn": 60 * 420 + 10 * 30 + 200, "disp": 120000, "pvc": 60 * 66 + 10 * 90 + 500, "t1": 60 * 60 + 10 * 75 + 400}
+# aslnn with the two 10x10 products per row on the tensor cores (the default, "nn" / "nn_tc"): the 200 FMAs per row leave
+# the FP32 pipe, the 40 tanh MUFU pairs per row stay -> the XU pipe is the binding roofline of that kernel
+LANE_INSTR = {"nn_tc": 60 * 220 + 10 * 30 + 200, "nn_fp32": 60 * 420 + 10 * 30 + 200, "sim_art": 60 * 50 + 10 * 60 + 300, "real_like": 60 * 21 + 10 * 30 + 200, "spatial": 60 * 21 + 10 * 30 + 200,
+              "nn": 60 * 220 + 10 * 30 + 200, "disp": 120000, "pvc": 60 * 66 + 10 * 90 + 500, "t1": 60 * 60 + 10 * 75 + 400}
 MUFU = {"nn_tc": 60 * 40 + 10 * 3 + 10 * 2 * 4, "nn_fp32": 60 * 40 + 10 * 3 + 10 * 2 * 4, "sim_art": 60 * 3 + 10 * 4 + 10 * 3 * 4, "real_like": 60 * 1 + 10 * 3 + 10 * 2 * 4, "spatial": 60 * 1 + 10 * 3 + 10 * 2 * 4,
         "nn": 60 * 40 + 10 * 3 + 10 * 2 * 4, "disp": None, "pvc": None, "t1": None}
 

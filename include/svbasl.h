@@ -57,8 +57,11 @@ extern "C" {
 #define SVBASL_F_ARTONLY 0x40      /* artonly: no tissue component */
 #define SVBASL_F_DISP_INFER 0x80   /* aslrest_disp infer_disp_params: s, sp are parameters */
 #define SVBASL_F_DISP_ASWRITTEN 0x100 /* reproduce gamma2-gamma2 == 0 (aslrest_disp.py:108) */
-#define SVBASL_F_NN_TC 0x200       /* aslnn: the two 10x10 products of the fused step on the tensor cores (tcgen05,
-                                      csrc/model_nn_tc.cuh; B = 6 register-resident batches, else the FP32-pipe kernel) */
+#define SVBASL_F_NN_TC 0x200       /* aslnn: the two 10x10 products per row of the fused step (the tf.matmul chain of
+                                      aslnn.py:238-260 and its gradient) on the tensor cores: tcgen05.mma kind::f16 with
+                                      hi/lo split operands staged in tensor memory, float32 accumulation
+                                      (csrc/model_nn_tc.cuh).  Without the flag the FP32-pipe kernel runs; both give
+                                      the same results to float32 rounding. */
 
 /* parameter transforms (svb dist: Normal / LogNormal / FoldedNormal) */
 #define SVBASL_XF_IDENTITY 0

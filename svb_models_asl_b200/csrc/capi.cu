@@ -63,9 +63,8 @@ static const KernelEntry *find_entry(const svbasl_model *m, int nbt, bool want_e
             if (score > best_score) { best = e; best_score = score; }
         }
     }
-    // the tensor-core variant exists for the register-resident batch size only
+    // no tensor-core instantiation for this call: the FP32-pipe kernel computes the same thing
     if (!best && allow_tc && (f & SVBASL_F_NN_TC) && m->kind == SVBASL_MODEL_ASLNN) return find_entry(m, nbt, want_eval, flavour, false);
-    if (best && (f & SVBASL_F_NN_TC) && best->nbt != nbt && allow_tc) return find_entry(m, nbt, want_eval, flavour, false);
     return best;
 }
 

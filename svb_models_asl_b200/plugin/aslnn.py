@@ -21,8 +21,9 @@ from .aslrest import AslRestModel, __version__
 LAYERS = [(2, 10), (10, 10), (10, 1)]           # aslnn.py:238-240
 
 
-# fused step on tcgen05 by default?  (measured: profiles/r2_notes.md section 4)
-TENSOR_CORE_STEP_DEFAULT = False
+# fused step on tcgen05 by default: 1.33 G against 1.15 G voxel-iters/s for the FP32-pipe kernel, same results to
+# float32 rounding (profiles/r2_notes.md section 4)
+TENSOR_CORE_STEP_DEFAULT = True
 
 
 class AslNNModel(Model):
@@ -90,10 +91,11 @@ class AslNNModel(Model):
         from ..ops import evaluate_model, nn_evaluate_tc
         if self.trained_weights is None:
             self._init_nn()
-        # Two kernels give the same result: the FP32-pipe one (csrc/model_nn.h) and the tcgen05 tensor-core one
-        # (csrc/nn_tc.cu).  For a 10-wide layer the tensor-core tile pipeline costs more issue slots (operand
-        # split, STS, TMEM load, barriers) than the 100 FMAs it replaces - measured 35 vs 65 G rows/s on a B200
-        # (profiles/r1_notes.md) - so the FP32 pipe is the default and `use_tensor_cores=True` selects the other.
+        # Two kernels give the same result: the FP32-pipe one (csrc/model_nn.h) and the stand-alone tcgen05 one
+        # (csrc/nn_tc.cu, A tiles through shared memory).  For the forward pass alone - one 10x10 product per row,
+        # nothing else to amortise the tile round trip over - the FP32 pipe is faster (65-69 against 49-52 G rows/s,
+        # profiles/r2_notes.md section 4) and is the default; `use_tensor_cores=True` selects the other.  The fused
+        # SVB step is a different matter: see `tensor_core_step` / kernel_model().
         if getattr(self, "use_tensor_cores", False):
             return nn_evaluate_tc(self, params, tpts)
         return evaluate_model(self, params, tpts)

@@ -85,21 +85,26 @@ def _nn_problem(golden, W, rng):
     return spec, prob
 
 
-def test_fused_step_with_tensor_core_products_matches_oracle(golden, record_error):
+@pytest.mark.parametrize("B", [6, 5, 1])
+def test_fused_step_with_tensor_core_products_matches_oracle(golden, record_error, B):
     """The fused ELBO + gradient of aslnn with the two 10x10 products per row on tcgen05 (csrc/model_nn_tc.cuh;
     SVBASL_F_NN_TC): cost and gradient against the oracle (autograd through the MLP, aslnn.py:238-260) at the north-star
-    tolerances, on 300 voxels = two full 128-row tiles and a ragged one."""
+    tolerances, on 300 voxels = two full 128-row tiles and a ragged one.  B = 6 is the register-resident instantiation
+    (three rounds of two time points), B = 5 and 1 the any-batch-size one with a single-row last round."""
     from tests.test_kernel_parity import _check_grads, _record_grad_errors
     be = H.Backend("cuda")
     rng = np.random.default_rng(44)
     W = 300
     spec, prob = _nn_problem(golden, W, rng)
+    if B != 6:
+        spec = H.nn_spec(spec.cfg["weights"], spec.cfg["biases"], latent="numeric", t_full=B)
+        prob = dict(prob, tpts=prob["tpts"][:B], data=prob["data"][:B])
     eps = rng.normal(size=(3, spec.n_samples, W)).astype(np.float32)
     ocost, ograd, _gh, _ = H.oracle_cost_grad(spec, prob, eps)
     m = be.model_desc(dict(spec.cfg, tensor_cores=True))
     e, _b = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], eps)
     cost, grad, _ = be.elbo_grad(m, e, spec.n_state)
-    _record_grad_errors(record_error, "nn_tc_fused/cuda", cost, grad, ocost, ograd)
+    _record_grad_errors(record_error, "nn_tc_fused/B%d/cuda" % B, cost, grad, ocost, ograd)
     _check_grads(cost, grad, ocost, ograd)
 
 
