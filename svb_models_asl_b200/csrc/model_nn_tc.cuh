@@ -58,6 +58,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 // the leading 11 significant bits of x: exactly representable in fp16 (for |x| >= 2^-14; below that the conversion
 // rounds and the error is below 2^-25 absolute)
 __device__ __forceinline__ float f16_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// two tanh from ONE reciprocal: 1/a0 = a1/(a0 a1), 1/a1 = a0/(a0 a1).  The tensor-core step is bound by the XU pipe
+// (40 MUFU per row for 20 tanh, ncu: 73 % busy, mio_throttle the top stall) while the FP32 pipe idles at 30 %: this
+// trades a quarter of the MUFU work for 4 FP32/ALU instructions per pair.  2^zc is capped at 2^62 so that the product
+// of two denominators stays finite (tanh is 1 to float32 precision long before).
+__device__ __forceinline__ void tanh_pair_c(float zc0, float zc1, float &t0, float &t1) {
+    float e0, e1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(zc0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(zc1));
+    const float a0 = fminf(e0, 4.611686018427388e18f) + 1.0f, a1 = fminf(e1, 4.611686018427388e18f) + 1.0f;
+    const float r = __fdividef(1.0f, a0 * a1);
+    t0 = fmaf(-2.0f, r * a1, 1.0f);
+    t1 = fmaf(-2.0f, r * a0, 1.0f);
+}
 __device__ __forceinline__ uint32_t pack2(float e0, float e1) {      // e0 in the low half = the lower K index
     const __half2 h = __floats2half2_rn(e0, e1);
     return *reinterpret_cast<const uint32_t *>(&h);
@@ -201,10 +214,10 @@ struct AslNNTC : AslNN {
     static __device__ __forceinline__ void stage_row(const NNWeights &w, const Sample &s, const Vox &v, float t, int slot) {
         float h1[H], g1[H];
 #pragma unroll
-        for (int j = 0; j < H; ++j) {
-            const float h = ftanh_c(w.w0t_c[j] * t + s.a1[j]);
-            h1[j] = h;
-            g1[j] = 1.0f - h * h;
+        for (int j = 0; j < H; j += 2) {
+            nntc::tanh_pair_c(w.w0t_c[j] * t + s.a1[j], w.w0t_c[j + 1] * t + s.a1[j + 1], h1[j], h1[j + 1]);
+            g1[j] = 1.0f - h1[j] * h1[j];
+            g1[j + 1] = 1.0f - h1[j + 1] * h1[j + 1];
         }
         const uint32_t base = v.tlane + (uint32_t)slot * 2u * nntc::kColsA;
         store_row(base, h1, 0x3C003C00u);                          // (1, 1): the bias columns
@@ -265,10 +278,13 @@ struct AslNNTC : AslNN {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float out = w.b2, dout = 0.0f;
 #pragma unroll
-        for (int k = 0; k < H; ++k) {
-            const float h = ftanh_c(__uint_as_float(r[k]));               // D1 = 2 log2(e) (W1^T h1 + b1)
-            out += w.w2[k] * h;
-            dout += __uint_as_float(r[nntc::kN + k]) * (1.0f - h * h);      // D2 = W2[k] * dz2[k]
+        for (int k = 0; k < H; k += 2) {
+            float ha, hb;
+            nntc::tanh_pair_c(__uint_as_float(r[k]), __uint_as_float(r[k + 1]), ha, hb);   // D1 = 2 log2(e) (W1^T h1 + b1)
+            out += w.w2[k] * ha;
+            out += w.w2[k + 1] * hb;
+            dout += __uint_as_float(r[nntc::kN + k]) * (1.0f - ha * ha);    // D2 = W2[k] * dz2[k]
+            dout += __uint_as_float(r[nntc::kN + k + 1]) * (1.0f - hb * hb);
         }
         float d[PA];
         d[0] = out;
