@@ -597,7 +597,7 @@ def main():
         fit.lo, fit.hi = 0, W                                           # every rank owns its own W voxels (weak scaling)
     n_t = len(PLDS) * reps
     n_batches = int(math.ceil(n_t / (wl["batch"] or n_t)))
-    ipl = max(1, min(args.iters_per_launch, 64)) if (n_batches == 1 and not cube) else 1
+    ipl = max(1, min(args.iters_per_launch, 64)) if not cube else 1     # spatial priors: one iteration per launch
     est_iters = (3 * (K + WU) + 64) * ipl + 200_000
     fit._setup(model.tpts(), dm.data_flattened, wl["batch"], FIT_OPTIONS["sample_size"], FIT_OPTIONS["learning_rate"],
                epochs=est_iters, force_num_latent_loss=FIT_OPTIONS["force_num_latent_loss"],
@@ -607,7 +607,9 @@ def main():
     f.n_vox_global = W if cube else W * world
     W_total = W if cube else W * world
     n_state = f.n_state
-    bytes_per_voxel = 8 * f.B + 24 * n_state          # data+tpts read; state/m/v read + written, per launch
+    # data+tpts read (one batch per launch when every iteration sees the same batch, else one per fused iteration);
+    # state/m/v read + written once per launch
+    bytes_per_voxel = 8 * f.B * (1 if n_batches == 1 else ipl) + 24 * n_state
     lane_instr = LANE_INSTR[args.workload]
     mufu = MUFU[args.workload]
 
@@ -630,7 +632,7 @@ def main():
         s_ms, s_per = timed_steps(D, torch, lambda: f.step(1), K)
         single = {"iters_per_launch": 1, "launches": K, "value": W_total * K / (s_ms * 1e-3), "unit": "voxel-iters/s",
                   "ms_per_iteration": s_ms / K, "avg_launch_ms": s_per,
-                  "hbm_gbs": bytes_per_voxel * f.n_vox / (s_per * 1e-3) / 1e9}
+                  "hbm_gbs": (8 * f.B + 24 * n_state) * f.n_vox / (s_per * 1e-3) / 1e9}
 
     # ---- sustained: the headline launches for >= 2 s, SM clocks of every rank ----
     n_sus, sus_ms, sus_clocks = sustained_leg(D, torch, step_fn, per_launch_ms, local_rank, seconds=args.sustained_seconds,

@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(32 * kDwWarps, 16 / kDwWarps) disp_warp_kernel
 // tau a whole number of grid steps, one iteration per launch)
 inline bool disp_warp_eligible(const StepArgs &a, bool tissue) {
     if (!tissue || a.e.n_samples > kDwSMax || a.e.n_batch > kDwBMax || a.md.conv_nt > kDwNtMax || a.md.conv_nt < 2) return false;
-    if (a.update && a.ad.n_iters != 1) return false;
+    if (a.update && a.ad.n_iters > 1 && a.e.step_dev) return false;   // fused iterations are launched one by one from the host
     for (int i = 0; i < a.e.n_par && i < SVBASL_MAX_PAR; ++i)
         if (a.e.prior_type[i] == SVBASL_PRIOR_MRF) return false;
     const float m = a.md.tau * a.md.conv_inv_h;
@@ -762,11 +762,26 @@ int launch_step_disp(const StepArgs &a, cudaStream_t st) {
     if (!force_scalar && disp_warp_eligible(a, M::TISS)) {
         // 8 warps per CTA (two CTAs per SM); 4 when the per-warp tables of a large S / grid / batch do not fit
         const char *wenv = getenv("SVBASL_DW_WARPS");               // measurement switch
-        int rc = 1;
-        if (wenv && wenv[0] == '1' && wenv[1] == '6') rc = launch_step_disp_warp<M, FL, 16>(a, st);
-        if (rc > 0 && !(wenv && wenv[0] == '4')) rc = launch_step_disp_warp<M, FL, kDwWarpsDefault>(a, st);
-        if (rc > 0) rc = launch_step_disp_warp<M, FL, 4>(a, st);
-        if (rc <= 0) return rc;
+        // svbasl_adam.n_iters fused iterations: the warp kernel keeps nothing on chip between iterations that would
+        // pay for fusing them (its state rows are 1 % of its time), so they are n_iters launches of the same call
+        const int n_iters = a.update ? a.ad.n_iters : 1;
+        StepArgs b = a;
+        b.ad.n_iters = 1;
+        for (int it = 0; it < n_iters; ++it) {
+            b.step = a.step + it;
+            b.cost_sum = a.cost_sum ? a.cost_sum + it : nullptr;
+            int rc = 1;
+            if (wenv && wenv[0] == '1' && wenv[1] == '6') rc = launch_step_disp_warp<M, FL, 16>(b, st);
+            if (rc > 0 && !(wenv && wenv[0] == '4')) rc = launch_step_disp_warp<M, FL, kDwWarpsDefault>(b, st);
+            if (rc > 0) rc = launch_step_disp_warp<M, FL, 4>(b, st);
+            if (rc < 0) return rc;
+            if (rc > 0) {
+                if (it == 0) break;                                 // does not fit at all: the thread-per-voxel kernel
+                return SVBASL_E_CUDA;
+            }
+            if (it == n_iters - 1) return 0;
+            if (b.e.state_out) b.e.state = b.e.state_out;           // the next iteration continues from what this one wrote
+        }
     }
     return launch_step<M, 0, FL>(a, st);
 }

@@ -771,3 +771,46 @@ def test_disp_warp_per_voxel_kernel_equals_thread_per_voxel_kernel(case, record_
     assert rows <= 5e-5, rows
     assert sw == pytest.approx(ss, rel=1e-5) and ssw[0] == pytest.approx(sss[0], rel=1e-5)
     assert np.abs(sts - prob["state"]).max() > 1e-3 and H.rel_err(stw, sts).max() <= 2e-4
+
+
+@pytest.mark.gpu
+def test_disp_fused_iterations_equal_single_launches():
+    """svbasl_adam.n_iters > 1 for aslrest_disp (what SvbFit.train asks for by default): the warp-per-voxel kernel is
+    launched once per iteration inside the one C call - same posterior, bit for bit, as n_iters calls of one iteration,
+    with strided mini-batches (n_batches = 8) and in-kernel draws; and close to the thread-per-voxel kernel's."""
+    be = H.Backend("cuda")
+    cfg = _disp_cfg("casl_tiss_art")
+    rng = np.random.default_rng(77)
+    W = 90
+    spec = H.aslrest_spec(cfg, n_samples=10, t_full=48)
+    prob = H.synth_problem(cfg, spec, W, rng, repeats=8, noise_sd=0.5)
+    m = be.model_desc(cfg)
+    finals, sums = {}, {}
+    for which in ("fused", "single", "scalar_fused"):
+        if which == "scalar_fused":
+            os.environ["SVBASL_DISP_SCALAR"] = "1"
+        try:
+            e, bufs = be.engine_desc(spec, prob["state"], prob["data"], prob["tpts"], None, n_batch=6, t_row0=0,
+                                     t_row_stride=8, seed=5)
+            if which == "single":
+                cs = []
+                ad, _ab = be.adam_desc(spec.n_state, W, 0.05, 8, step0=0, n_iters=1, n_batches=8)
+                for it in range(4):
+                    ad.step0 = it
+                    s_sum, nanc = be.step(m, e, ad)
+                    assert nanc == 0
+                    cs.append(float(s_sum[0]))
+                sums[which] = np.array(cs)
+            else:
+                ad, _ab = be.adam_desc(spec.n_state, W, 0.05, 8, step0=0, n_iters=4, n_batches=8)
+                s_sum, nanc = be.step(m, e, ad)
+                assert nanc == 0
+                sums[which] = np.array([float(x) for x in s_sum[:4]])
+            finals[which] = be.get(bufs["state"])
+        finally:
+            os.environ.pop("SVBASL_DISP_SCALAR", None)
+    np.testing.assert_array_equal(finals["fused"], finals["single"])
+    np.testing.assert_array_equal(sums["fused"], sums["single"])
+    assert np.abs(finals["fused"] - prob["state"]).max() > 1e-2
+    stats = H.trajectory_error(finals["fused"], finals["scalar_fused"])
+    assert stats["q50"] <= 2e-6 and stats["q99"] <= 1e-3, stats
