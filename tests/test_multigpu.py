@@ -2,7 +2,9 @@
 Two ranks / two GPUs (NCCL over NVLink) against one GPU, through svb.main.run:
 * voxel-wise priors: shards are independent, results equal the single-GPU fit voxel for voxel
   (the Philox stream is keyed on the GLOBAL voxel id);
-* spatial prior: halo state exchange (ncclSend/Recv) + all-reduce of the log-ak gradient every iteration.
+* spatial prior: the halo holds the neighbour ranks' boundary SAMPLES of every iteration - stored by the drawing kernel
+  straight into the neighbour's halo columns over NVLink peer memory ("peer"), or sent with ncclSend/Recv ("nccl") -
+  and the log-ak gradient is all-reduced every iteration (peer-memory mailboxes, or NCCL: "peer+nccl" / "nccl").
 Skipped unless the box has at least two GPUs (gpurun --gpus 2).
 """
 import os
