@@ -26,7 +26,9 @@ SVB_D float fsqrt(float x) {                               // sqrt.approx: MUFU.
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+SVB_D float flog2(float x) { return __log2f(x); }          // MUFU.LG2
 SVB_D void fsincos2pi(float u, float *s, float *c) { __sincosf(6.283185307179586f * u, s, c); }
+SVB_D void fsincos(float x, float *s, float *c) { __sincosf(x, s, c); }     // FMUL.RZ (to turns) + MUFU.SIN + MUFU.COS
 SVB_D uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 SVB_D float ferf(float x) { return erff(x); }
 SVB_D float ftanh(float x) {                               // 1 - 2/(exp(2x)+1): ~2 ulp, MUFU.EX2 + MUFU.RCP
@@ -51,6 +53,11 @@ SVB_HD void fsincos2pi(float u, float *s, float *c) {
     float a = 6.283185307179586f * u;
     *s = sinf(a);
     *c = cosf(a);
+}
+SVB_HD float flog2(float x) { return log2f(x); }
+SVB_HD void fsincos(float x, float *s, float *c) {
+    *s = sinf(x);
+    *c = cosf(x);
 }
 SVB_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
 SVB_HD float ferf(float x) { return erff(x); }

@@ -83,6 +83,7 @@ struct DevModel {
     float att, attwm, fwm, artt;
     float fc_pc, fc_pc_wm;            // fcalib/pc
     float leadscale, inv_leadscale, inv_leadscale_s;   // _s: times sqrt(log2 e)
+    float tau_inv_leadscale_s, inv_leadscale_pi;       // tau * inv_leadscale_s; inv_leadscale / sqrt(pi)
     TissueRates gm, wm;               // for the fixed t1 / t1wm of the options
     float pvgm_s, pvwm_s;
     const float *pvgm, *pvwm;
@@ -110,6 +111,8 @@ inline DevModel make_dev_model(const svbasl_model &m) {
     d.leadscale = m.leadscale;
     d.inv_leadscale = m.leadscale != 0.0f ? 1.0f / m.leadscale : 0.0f;
     d.inv_leadscale_s = d.inv_leadscale * 1.2011224087864498f;
+    d.tau_inv_leadscale_s = m.tau * d.inv_leadscale_s;
+    d.inv_leadscale_pi = d.inv_leadscale * 0.5641895835477563f;
     const bool casl = (m.flags & SVBASL_F_CASL) != 0;
     d.gm = tissue_rates((m.t1 > 0.0f ? 1.0f / m.t1 : 0.0f) + d.fc_pc, m.tau, d.inv_t1b, casl);
     d.wm = tissue_rates((m.t1wm > 0.0f ? 1.0f / m.t1wm : 0.0f) + d.fc_pc_wm, m.tau, d.inv_t1b, casl);

@@ -37,6 +37,22 @@ SVB_HD void erf_step_scaled(float zs, float &half_1p_erf, float &gauss) {
     gauss = 0.5641895835477563f * g0;
 }
 
+// The same step for callers that fold the Gaussian's constant 1/sqrt(pi) into their own factors: returns
+// 1/2 (1 + erf z) and the bare exp(-z^2).
+SVB_HD void erf_step_raw(float zs, float &half_1p_erf, float &g0) {
+    const float a = fmin2(fabsf(zs), 9.6f);
+    const float t = frcp(1.0f + (0.3275911f / SVB_SQRT_LOG2E) * a);
+    float p = 0.5f * 1.061405429f;
+    p = p * t - 0.5f * 1.453152027f;
+    p = p * t + 0.5f * 1.421413741f;
+    p = p * t - 0.5f * 0.284496736f;
+    p = p * t + 0.5f * 0.254829592f;
+    g0 = fexp2(-a * a);
+    const float half_erfc = (p * t) * g0;
+    half_1p_erf = zs >= 0.0f ? 1.0f - half_erfc : half_erfc;
+}
+#define SVB_INV_SQRT_PI 0.5641895835477563f
+
 template <uint32_t F>
 struct AslRest {
     static constexpr bool CASL = (F & SVBASL_F_CASL) != 0;
@@ -99,15 +115,20 @@ struct AslRest {
         float delt, tdp;      // delta, fl(tau + delta)             (mask thresholds, aslrest.py:362-363)
         float A;              // CASL: 2*T1app*exp(-delta/t1b) (aslrest.py:371); PASL: 2*exp(r*delta)
         float AE;             // CASL with eb[]: A * exp(delta/T1app), so that A*E = AE * eb[b]
+        float Ab;             // CASL: -A / t1b, the constant of dS_during/ddelta = (1/t1b - q) F E - A/t1b
         float pvf, pv;        // pv*f, pv
         float dqdt1;          // dq/dt1 = -1/t1^2
     };
 
     struct Sample {
         Tissue gm, wm;
-        float fb, deltb, kc, dkc;                     // arterial (aslrest.py:404-407)
-        float thr_out, inv_ls_s, dz_in_c, dz_in_t;   // lead-in/out (aslrest.py:411-419); _s: x sqrt(log2 e)
-        bool leadin_ok;
+        // arterial (aslrest.py:404-419).  The time loop produces RAW terms: for CASL the per-sample factor
+        // kc = 2 exp(-deltblood/t1b) is applied after the loop (fbk = fblood kc on the prediction, scale_grads on the
+        // derivative sums); the Gaussian's 1/sqrt(pi) sits in the dz factors.
+        float fb, fbk, deltb, kc;
+        float thr_out;            // lead-out begins at deltblood + tau/2                         (aslrest.py:411)
+        float zin_a, zin_b;       // lead-in: z sqrt(log2 e) = zin_a (t - deltblood) + zin_b      (aslrest.py:413-423)
+        float dzin_c, dzin_t;     // lead-in: dz/ddeltblood / sqrt(pi) = dzin_c + dzin_t t
     };
 
     static SVB_HD Vox load_vox(const DevModel &m, int64_t w) {
@@ -134,6 +155,7 @@ struct AslRest {
         }
         ts.A = CASL ? ts.k.two_iq * fexp(-delt * m.inv_t1b) : 2.0f * fexp(ts.k.r * delt);
         ts.AE = (CASL && !T1_SAMPLED) ? ts.k.two_iq * fexp(delt * (ts.k.q - m.inv_t1b)) : 0.0f;
+        ts.Ab = CASL ? -ts.A * m.inv_t1b : 0.0f;
     }
 
     // x[P]: model-space parameter values for this sample
@@ -153,17 +175,21 @@ struct AslRest {
             s.fb = x[ix(I_FBLOOD)];
             const float db = (I_DELTBLOOD >= 0) ? x[ix(I_DELTBLOOD)] : m.artt;
             s.deltb = db;
-            s.kc = CASL ? 2.0f * fexp(-db * m.inv_t1b) : 0.0f;
-            s.dkc = -s.kc * m.inv_t1b;
+            s.kc = CASL ? 2.0f * fexp(-db * m.inv_t1b) : 1.0f;
+            s.fbk = CASL ? s.fb * s.kc : s.fb;
             s.thr_out = db + m.half_tau;
             const float ls = fmin2(db, m.leadscale);
-            s.leadin_ok = ls > 0.0f;
+            const bool leadin_ok = ls > 0.0f;                                     // aslrest.py:419
             // tf.minimum routes the gradient to deltblood when it is the smaller argument: z_in = t/db - 1
             const bool own = db <= m.leadscale;
-            const float ils = own ? frcp(s.leadin_ok ? ls : 1.0f) : m.inv_leadscale;
-            s.inv_ls_s = ils * SVB_SQRT_LOG2E;
-            s.dz_in_c = own ? 0.0f : -ils;
-            s.dz_in_t = own ? -ils * ils : 0.0f;
+            const float ils = own ? frcp(leadin_ok ? ls : 1.0f) : m.inv_leadscale;
+            // Without a lead-in (leadscale or deltblood <= 0) the signal before the lead-out is zero: z is pinned at
+            // the clamp of the error-function step (1/2 erfc(8) ~ 1e-29) and its derivative terms vanish, which
+            // spares the time loop a select per element.
+            s.zin_a = leadin_ok ? ils * SVB_SQRT_LOG2E : 0.0f;
+            s.zin_b = leadin_ok ? 0.0f : -9.6f;
+            s.dzin_c = (own || !leadin_ok) ? 0.0f : -ils * SVB_INV_SQRT_PI;
+            s.dzin_t = (own && leadin_ok) ? -ils * ils * SVB_INV_SQRT_PI : 0.0f;
         }
         return s;
     }
@@ -181,8 +207,8 @@ struct AslRest {
             const float FE = USE_EB ? ts.AE * ebt : ts.A * fexp2(u * ts.k.nk);
             const float Sd = ts.A - FE;                    // aslrest.py:372
             const float Sp = FE * ts.k.c1;                 // aslrest.py:373 with exp(tau q) folded into c1
-            const float dd = -Sd * m.inv_t1b - FE * ts.k.q;
-            const float dp = Sp * (ts.k.q - m.inv_t1b);
+            const float dd = FE * (m.inv_t1b - ts.k.q) + ts.Ab;          // -Sd/t1b - F E q with Sd = A - F E
+            const float dp = FE * (ts.k.c1 * (ts.k.q - m.inv_t1b));
             S = post ? Sp : (during ? Sd : 0.0f);
             dSdd = post ? dp : (during ? dd : 0.0f);
             if (WANT_Q) {
@@ -236,19 +262,24 @@ struct AslRest {
             if (I_T1WM >= 0) d[ix(I_T1WM)] = 0.0f;
         }
         if (ART) {
-            const float kc = CASL ? s.kc : 2.0f * fexp(-t * m.inv_t1b);     // aslrest.py:404-407
-            const float dkc = CASL ? s.dkc : 0.0f;
             const bool leadout = t > s.thr_out;                             // aslrest.py:411
-            const bool active = leadout || s.leadin_ok;                     // aslrest.py:419
             const float u = t - s.deltb;
-            // z of aslrest.py:422-423, scaled by sqrt(log2 e) for erf_step_scaled
-            const float zs = leadout ? (m.tau - u) * m.inv_leadscale_s : u * s.inv_ls_s;
-            const float dz = leadout ? m.inv_leadscale : (s.dz_in_c + s.dz_in_t * t);
-            float h, g;
-            erf_step_scaled(zs, h, g);
-            const float A = active ? kc * h : 0.0f;
-            const float dA = active ? (dkc * h + kc * g * dz) : 0.0f;
-            pred += s.fb * A;
+            // z of aslrest.py:422-423 times sqrt(log2 e) (erf_step_raw) as za u + zb, lead-out: (tau - u)/leadscale
+            const float za = leadout ? -m.inv_leadscale_s : s.zin_a;
+            const float zb = leadout ? m.tau_inv_leadscale_s : s.zin_b;
+            const float dz = leadout ? m.inv_leadscale_pi : (s.dzin_c + s.dzin_t * t);     // dz/ddeltblood / sqrt(pi)
+            float h, g0;
+            erf_step_raw(za * u + zb, h, g0);
+            float A, dA;
+            if (CASL) {                                                     // kc = 2 exp(-deltblood/t1b): per sample
+                A = h;
+                dA = g0 * dz - m.inv_t1b * h;
+            } else {                                                        // kc = 2 exp(-t/t1b)   (aslrest.py:404-407)
+                const float kc = 2.0f * fexp(-t * m.inv_t1b);
+                A = kc * h;
+                dA = kc * (g0 * dz);
+            }
+            pred += s.fbk * A;
             d[ix(I_FBLOOD)] = A;
             if (I_DELTBLOOD >= 0) d[ix(I_DELTBLOOD)] = dA;
         }
@@ -264,7 +295,10 @@ struct AslRest {
             if (I_DELTWM >= 0 && INCWM) G[ix(I_DELTWM)] *= s.wm.pvf;
             if (I_T1WM >= 0 && INCWM) G[ix(I_T1WM)] *= s.wm.pvf * s.wm.dqdt1;
         }
-        if (ART && I_DELTBLOOD >= 0) G[ix(I_DELTBLOOD)] *= s.fb;
+        if (ART) {
+            if (CASL) G[ix(I_FBLOOD)] *= s.kc;
+            if (I_DELTBLOOD >= 0) G[ix(I_DELTBLOOD)] *= s.fbk;
+        }
     }
 
     // forward value only (Model.evaluate)

@@ -30,8 +30,23 @@ SVB_HD uint32_t rng_key(uint64_t seed, int64_t step) {
            ((uint32_t)((uint64_t)step >> 32) * 0xC2B2AE3Du);
 }
 
-// uniform in (0,1): 24 random bits, never 0 or 1
+// uniform in (0,1): 24 random bits, never 0 or 1 (slow paths and tests; the Box-Muller pair below converts the full
+// 32-bit words itself)
 SVB_HD float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f + 2.98023223876953125e-08f; }
+
+// Box-Muller pair from two 32-bit words in 12 instructions: u = (x + 1/2) 2^-32 straight from the unsigned-to-float
+// conversion (one I2FP + one FFMA per word; the conversion rounds to nearest, so u lies in [2^-33, 1] and the
+// radius in [0, 6.8]), the radius as sqrt(-2 ln2 * lg2 u) (MUFU.LG2, FMUL, MUFU.SQRT) and the angle with 2 pi
+// folded into the conversion's FFMA.
+SVB_HD void box_muller(uint32_t a, uint32_t b, float &n0, float &n1) {
+    const float ua = (float)a * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
+    const float ang = (float)b * (6.283185307179586f * 2.3283064365386963e-10f) + (6.283185307179586f * 1.1641532182693481e-10f);
+    const float rad = fsqrt(-1.3862943611198906f * flog2(ua));
+    float sn, cs;
+    fsincos(ang, &sn, &cs);
+    n0 = rad * cs;
+    n1 = rad * sn;
+}
 
 // The stream of one (voxel, step): normals numbered q = j*S2 + s (posterior row j, sample s; S2 = S rounded up to
 // even).  Normals 2p and 2p+1 are the Box-Muller pair of ONE Philox call with counter (global voxel, p): a call
@@ -41,11 +56,7 @@ SVB_HD float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f 
 SVB_HD void normal_pair(uint32_t key, int64_t vox_global, int pair, float &n0, float &n1) {
     uint32_t a, b;
     philox2x32_10((uint32_t)vox_global, (uint32_t)pair ^ ((uint32_t)((uint64_t)vox_global >> 32) << 24), key, a, b);
-    const float rad = fsqrt(-2.0f * flog(u01(a)));
-    float sn, cs;
-    fsincos2pi(u01(b), &sn, &cs);
-    n0 = rad * cs;
-    n1 = rad * sn;
+    box_muller(a, b, n0, n1);
 }
 
 SVB_HD int stream_pair(int j, int s, int S) { return (j * ((S + 1) >> 1)) + (s >> 1); }

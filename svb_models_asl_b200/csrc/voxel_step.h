@@ -14,6 +14,10 @@
 #include "philox.h"
 #include "dev_model.h"
 
+#ifndef SVB_PAIRED_SAMPLES
+#define SVB_PAIRED_SAMPLES 1
+#endif
+
 namespace svb {
 
 SVB_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }       // lower triangle incl. diagonal
@@ -124,6 +128,7 @@ template <class M, int NBT, int FL = 0>
 struct VoxelStep {
     static constexpr bool LEAN = FL != 0;           // numeric latent loss + Philox draws fixed at compile time
     static constexpr bool SPATIAL = FL != 1;
+    static constexpr bool PAIRED = SVB_PAIRED_SAMPLES;   // sample loop unrolled over the two samples of a Philox call
     static constexpr int P = M::P;
     static constexpr int N = P + 1;                 // noise last
     static constexpr int NL = N * (N - 1) / 2;
@@ -188,67 +193,74 @@ struct VoxelStep {
     }
 
     // Closing algebra of elbo_grad: from the sums over samples (a_mu = sum_s g_s, a_L = sum_s g_s eps_s^T,
-    // a_hyp = sum_s lw (theta - m)^2 / v or the MRF log-ak share, cost = sum_s of the per-sample cost) to the cost of
+    // a_hyp = sum_s (theta - m)^2 or the MRF log-ak share, cost = sum_s of the per-sample cost) to the cost of
     // the voxel and the gradients g_* (latent-loss constants, 1/S, entropy or closed-form KL, chain rule to logvar).
     SVB_HD float finish(const svbasl_engine &e, const EngineConst &ec, const Terms &t, float *a_mu, float *a_L, float *a_hyp,
                         float cost, bool numeric) {
         const int S = e.n_samples;
         const float lw = e.latent_weight;
         const float invS = ec.inv_s;
+        const float gs = e.grad_scale;
         const float *sd = t.sd, *pm = t.pm, *pinv = t.pinv, *plog = t.plog, *phi_live = t.phi_live;
         if (numeric) {
+            // Sample-based latent loss: every gradient is (1/S) x (sum over samples) plus, on the diagonal of L, the
+            // entropy term -1/2 log det(cov) = -sum_i log L_ii.  With L_ii = exp(logvar_i / 2) the chain rule turns its
+            // gradient -lw / L_ii into the constant -lw/2 per log-variance, so 1/S and grad_scale are applied as ONE
+            // factor to the raw sums.
+            const float kg = invS * gs;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 if (!SPATIAL || e.prior_type[i] != SVBASL_PRIOR_MRF) {
-                    const float q = a_hyp[i];                           // sum_s lw (theta-m)^2 / v
+                    const float q = t.lw_pinv[i] * a_hyp[i];            // sum_s lw (theta-m)^2 / v
                     cost += 0.5f * q + (float)S * lw * 0.5f * plog[i];
                     a_hyp[i] = 0.5f * (q - (float)S * lw);              // sum_s lw/2 ((theta-m)^2/v - 1)
                 }
             }
+            cost *= invS;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                cost -= lw * 0.5f * lv[i];
+                g_mu[i] = kg * a_mu[i];
+                g_lv[i] = (kg * a_L[tri(i, i)]) * (0.5f * sd[i]) - 0.5f * gs * lw;
+                g_lphi[i] = kg * a_hyp[i] * phi_live[i];
+                if (SPATIAL) ak_out[i] = invS * a_hyp[i];
+#pragma unroll
+                for (int j = 0; j < i; ++j) g_od[stri(i, j)] = kg * a_L[tri(i, j)];
+            }
+            return cost;
         }
         cost *= invS;
 #pragma unroll
         for (int i = 0; i < N; ++i) { a_mu[i] *= invS; a_hyp[i] *= invS; }
 #pragma unroll
         for (int k = 0; k < NT; ++k) a_L[k] *= invS;
-
-        if (numeric) {
-            // entropy term -1/2 log det(cov) = -sum_i log L_ii
+        // closed-form KL( N(mu, cov) || N(pm, diag(pv)) ), cov = L^T L (svb) or L L^T
+        float kl = 0.0f;
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                cost -= lw * 0.5f * lv[i];
-                a_L[tri(i, i)] -= lw * frcp(sd[i]);
-            }
-        } else {
-            // closed-form KL( N(mu, cov) || N(pm, diag(pv)) ), cov = L^T L (svb) or L L^T
-            float kl = 0.0f;
+        for (int i = 0; i < N; ++i) {
+            const float dm = mu[i] - pm[i];
+            float cii = 0.0f;     // cov_ii
+            if (e.cov_llt) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const float dm = mu[i] - pm[i];
-                float cii = 0.0f;     // cov_ii
-                if (e.cov_llt) {
-#pragma unroll
-                    for (int j = 0; j <= i; ++j) {
-                        const float l = (j == i) ? sd[i] : od[stri(i, j)];
-                        cii += l * l;
-                        a_L[tri(i, j)] += lw * l * pinv[i];
-                    }
-                } else {
-#pragma unroll
-                    for (int r = i; r < N; ++r) {
-                        const float l = (r == i) ? sd[i] : od[stri(r, i)];
-                        cii += l * l;
-                        a_L[tri(r, i)] += lw * l * pinv[i];
-                    }
+                for (int j = 0; j <= i; ++j) {
+                    const float l = (j == i) ? sd[i] : od[stri(i, j)];
+                    cii += l * l;
+                    a_L[tri(i, j)] += lw * l * pinv[i];
                 }
-                kl += cii * pinv[i] + dm * dm * pinv[i] - 1.0f + plog[i] - lv[i];
-                a_mu[i] += lw * dm * pinv[i];
-                a_L[tri(i, i)] -= lw * frcp(sd[i]);
-                a_hyp[i] = lw * 0.5f * (pinv[i] * (cii + dm * dm) - 1.0f);
+            } else {
+#pragma unroll
+                for (int r = i; r < N; ++r) {
+                    const float l = (r == i) ? sd[i] : od[stri(r, i)];
+                    cii += l * l;
+                    a_L[tri(r, i)] += lw * l * pinv[i];
+                }
             }
-            cost += lw * 0.5f * kl;
+            kl += cii * pinv[i] + dm * dm * pinv[i] - 1.0f + plog[i] - lv[i];
+            a_mu[i] += lw * dm * pinv[i];
+            a_L[tri(i, i)] -= lw * frcp(sd[i]);
+            a_hyp[i] = lw * 0.5f * (pinv[i] * (cii + dm * dm) - 1.0f);
         }
-        const float gs = e.grad_scale;
+        cost += lw * 0.5f * kl;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             g_mu[i] = gs * a_mu[i];
@@ -294,17 +306,9 @@ struct VoxelStep {
         for (int k = 0; k < NT; ++k) a_L[k] = 0.0f;
         float cost = 0.0f;
 
-        float spare[N];                                // second halves of the Box-Muller pairs: the next sample's draws
-#pragma unroll
-        for (int j = 0; j < N; ++j) spare[j] = 0.0f;
-        for (int s = 0; s < S; ++s) {
-            float eps[N];
-            if (eps_mem) {
-#pragma unroll
-                for (int j = 0; j < N; ++j) eps[j] = e.eps[((int64_t)j * S + s) * e.ld + w];
-            } else {
-                normal_row<N>(key, e.vox_offset + w, s, S, eps, spare);
-            }
+        // One sample: theta = mu + L eps, the model and its derivatives over the batch, the per-sample cost and the
+        // sums the closing algebra needs.
+        auto one_sample = [&](int s, const float *eps) {
             float th[N];
 #pragma unroll
             for (int i = 0; i < N; ++i) {
@@ -370,11 +374,10 @@ struct VoxelStep {
                         a_hyp[i] += lw * (-0.5f + 0.25f * ak * sdx2);
                     } else {
                         // -log N(theta; m, v) up to the constant 1/2 log v (added once after the loop);
-                        // a_hyp accumulates lw*(theta-m)^2/v, which is also the ARD log-phi gradient term
+                        // a_hyp accumulates (theta-m)^2; times lw/v (finish) it is also the ARD log-phi gradient term
                         const float dth = th[i] - pm[i];
-                        const float zz = dth * lw_pinv[i];
-                        g[i] += zz;
-                        a_hyp[i] += dth * zz;
+                        g[i] += dth * lw_pinv[i];
+                        a_hyp[i] += dth * dth;
                     }
                 }
             }
@@ -383,6 +386,32 @@ struct VoxelStep {
                 a_mu[i] += g[i];
 #pragma unroll
                 for (int j = 0; j <= i; ++j) a_L[tri(i, j)] += g[i] * eps[j];
+            }
+        };
+        if (eps_mem) {
+            for (int s = 0; s < S; ++s) {
+                float eps[N];
+#pragma unroll
+                for (int j = 0; j < N; ++j) eps[j] = e.eps[((int64_t)j * S + s) * e.ld + w];
+                one_sample(s, eps);
+            }
+        } else if (PAIRED) {
+            // a Philox call yields the same posterior row of two consecutive samples (philox.h): draw both, run both
+            for (int s = 0; s < S; s += 2) {
+                float ea[N], eb[N];
+#pragma unroll
+                for (int j = 0; j < N; ++j) normal_pair(key, e.vox_offset + w, stream_pair(j, s, S), ea[j], eb[j]);
+                one_sample(s, ea);
+                if (s + 1 < S) one_sample(s + 1, eb);
+            }
+        } else {
+            float spare[N];                            // second halves of the Box-Muller pairs: the next sample's draws
+#pragma unroll
+            for (int j = 0; j < N; ++j) spare[j] = 0.0f;
+            for (int s = 0; s < S; ++s) {
+                float eps[N];
+                normal_row<N>(key, e.vox_offset + w, s, S, eps, spare);
+                one_sample(s, eps);
             }
         }
         return finish(e, ec, tm, a_mu, a_L, a_hyp, cost, numeric);
@@ -414,8 +443,8 @@ struct VoxelStep {
     }
 
     static SVB_HD float adam1(const svbasl_adam &ad, float lr_t, float x, float g, float &m, float &v) {
-        m = ad.beta1 * m + (1.0f - ad.beta1) * g;
-        v = ad.beta2 * v + (1.0f - ad.beta2) * g * g;
+        m += (g - m) * (1.0f - ad.beta1);              // the form TensorFlow's ApplyAdam kernel evaluates
+        v += (g * g - v) * (1.0f - ad.beta2);
         return x - lr_t * fdiv(m, fsqrt(v) + ad.epsilon);
     }
 
