@@ -9,7 +9,7 @@ Workload (BASELINE.json configs[1], scripts/asl_example_sim.py + gen_test_data.p
 6 PLDs, ftiss + delttiss + arterial component (fblood ARD, deltblood), S = 10 samples, sample-based latent
 loss, 1,000,000 synthetic voxels PER GPU (weak scaling; voxels are independent so shards need no data-path
 collective).  A "step" is one launch of the fused kernel.  This workload has ONE time-point batch per epoch
-(T = B = 6), so a launch fuses `--iters-per-launch` (8) iterations: the state and the batch stay in registers and the
+(T = B = 6), so a launch fuses `--iters-per-launch` (16, the trainer's default) iterations: the state and the batch stay in registers and the
 Adam moments in shared memory between them (svbasl_adam.n_iters; bit-identical to single-iteration launches,
 tests/test_fit_gpu.py).  `value` = voxels x iterations / device time; the one-iteration-per-launch figure is reported
 beside it (`single_launch`).
@@ -523,7 +523,7 @@ def main():
     ap.add_argument("--reference-max-steps", type=int, default=8,
                     help="--impl reference: at most this many timed iterations over the full 1M voxels (~1-2 s each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--iters-per-launch", type=int, default=8,
+    ap.add_argument("--iters-per-launch", type=int, default=16,
                     help="iterations fused per launch when the workload has one time-point batch per epoch (state, "
                          "data and Adam moments stay on chip between them); 1 = one iteration per launch")
     ap.add_argument("--halo-mode", default="peer", choices=["peer", "peer+nccl", "nccl"],

@@ -370,9 +370,8 @@ __global__ void __launch_bounds__(32 * kDwWarps, 16 / kDwWarps) disp_warp_kernel
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 const float dth = th[i] - tm.pm[i];
-                const float zz = dth * tm.lw_pinv[i];
-                g[i] += zz;
-                pa_hyp[i] += dth * zz;
+                g[i] += dth * tm.lw_pinv[i];
+                pa_hyp[i] += dth * dth;                  // finish() applies lw / v
             }
         }
 #pragma unroll

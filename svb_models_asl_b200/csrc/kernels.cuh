@@ -130,6 +130,8 @@ struct is_cta_coop : std::false_type {};
 template <class M>
 struct is_cta_coop<M, std::void_t<decltype(M::kCtaCoop)>> : std::bool_constant<M::kCtaCoop> {};
 
+constexpr int kMaxDeferredCosts = 16;
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -174,6 +176,7 @@ template <class M, int NBT, int FL>
 __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __grid_constant__ StepArgs a) {
     extern __shared__ float mv_tile[];
     __shared__ float red[kBlock / 32];
+    __shared__ float red_it[kMaxDeferredCosts][kBlock / 32];
     typedef VoxelStep<M, NBT, FL> VS;
     constexpr bool LEAN = FL != 0;
     constexpr bool SPATIAL = FL != 1;
@@ -233,6 +236,9 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
         nbt.mask = mask;
     }
     const int n_iters = update ? a.ad.n_iters : 1;
+    // the per-iteration cost sums of a fused launch leave the CTA together after the last iteration: no CTA barrier
+    // inside the iteration loop
+    const bool defer_costs = n_iters > 1 && n_iters <= kMaxDeferredCosts;
     int skipped = 0;
     const int64_t step_base = a.e.step_dev ? (int64_t)*a.e.step_dev : a.step;   // device counter under graph replay
     double *cost_sum = a.cost_sum ? a.cost_sum + ((a.e.step_dev && !a.e.cost_sum_scalar) ? step_base : 0) : nullptr;
@@ -286,12 +292,28 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
         } else {
             cost = 0.0f;
         }
-        if (cost_sum) block_accumulate(cost, cost_sum + it, red);
+        if (cost_sum) {
+            if (defer_costs) {                               // warp sums now, the CTA's sum and its atomic after the loop
+                const float ws = warp_sum(cost);
+                if ((threadIdx.x & 31) == 0) red_it[it][threadIdx.x >> 5] = ws;
+            } else {
+                block_accumulate(cost, cost_sum + it, red);
+            }
+        }
         if (SPATIAL && a.e.ak_grad) {
 #pragma unroll
             for (int i = 0; i < VS::N; ++i)
                 if (a.e.prior_type[i] == SVBASL_PRIOR_MRF)
                     block_accumulate(live ? vs.ak_out[i] : 0.0f, a.e.ak_grad + a.ec.sp_slot[i], red);
+        }
+    }
+    if (cost_sum && defer_costs) {
+        __syncthreads();
+        if (threadIdx.x < n_iters) {
+            float t = 0.0f;
+#pragma unroll
+            for (int i = 0; i < kBlock / 32; ++i) t += red_it[threadIdx.x][i];
+            atomicAdd(cost_sum + threadIdx.x, (double)t);
         }
     }
     if (a.nan_count && skipped) atomicAdd((unsigned long long *)a.nan_count, (unsigned long long)skipped);

@@ -81,6 +81,7 @@ struct AslRest {
     static constexpr int I_DELTBLOOD = (ART && ATT) ? N_A + 1 : -1;
     static constexpr int P = N_A + (ART ? (1 + (ATT ? 1 : 0)) : 0);
     static constexpr bool kRegHeavy = false;
+    static constexpr bool kPairedSamples = true;      // voxel_step.h: both samples of a Philox call per loop trip
     static constexpr int PA = P > 0 ? P : 1;
 
     static constexpr int xf(int) { return SVBASL_XF_IDENTITY; }   // all Normal (aslrest.py:184-246)
@@ -127,7 +128,8 @@ struct AslRest {
         // derivative sums); the Gaussian's 1/sqrt(pi) sits in the dz factors.
         float fb, fbk, deltb, kc;
         float thr_out;            // lead-out begins at deltblood + tau/2                         (aslrest.py:411)
-        float zin_a, zin_b;       // lead-in: z sqrt(log2 e) = zin_a (t - deltblood) + zin_b      (aslrest.py:413-423)
+        float zin_a, zin_b;       // lead-in:  z sqrt(log2 e) = zin_a t + zin_b                   (aslrest.py:413-423)
+        float zout_b;             // lead-out: z sqrt(log2 e) = -t/leadscale' + zout_b            (aslrest.py:412,422)
         float dzin_c, dzin_t;     // lead-in: dz/ddeltblood / sqrt(pi) = dzin_c + dzin_t t
     };
 
@@ -187,7 +189,8 @@ struct AslRest {
             // the clamp of the error-function step (1/2 erfc(8) ~ 1e-29) and its derivative terms vanish, which
             // spares the time loop a select per element.
             s.zin_a = leadin_ok ? ils * SVB_SQRT_LOG2E : 0.0f;
-            s.zin_b = leadin_ok ? 0.0f : -9.6f;
+            s.zin_b = leadin_ok ? -db * s.zin_a : -9.6f;                          // z_in = (t - deltblood) / ls
+            s.zout_b = (m.tau + db) * m.inv_leadscale_s;                          // z_out = (tau + deltblood - t) / leadscale
             s.dzin_c = (own || !leadin_ok) ? 0.0f : -ils * SVB_INV_SQRT_PI;
             s.dzin_t = (own && leadin_ok) ? -ils * ils * SVB_INV_SQRT_PI : 0.0f;
         }
@@ -199,8 +202,10 @@ struct AslRest {
     template <bool WANT_Q, bool USE_EB>
     static SVB_HD void tissue_eval(const DevModel &m, const Tissue &ts, float t, float ebt, float &S, float &dSdd,
                                    float &dSdq) {
+        // the bolus has arrived / has passed (aslrest.py:362-363); tau >= 0, so `post` implies `arrived` and the
+        // three-way masks become two nested selects
         const bool post = t > ts.tdp;
-        const bool during = (t > ts.delt) && !post;
+        const bool arrived = t > ts.delt;
         const float u = t - ts.delt;
         if (CASL) {
             // A * exp(-(t-delta)/T1app)
@@ -209,12 +214,12 @@ struct AslRest {
             const float Sp = FE * ts.k.c1;                 // aslrest.py:373 with exp(tau q) folded into c1
             const float dd = FE * (m.inv_t1b - ts.k.q) + ts.Ab;          // -Sd/t1b - F E q with Sd = A - F E
             const float dp = FE * (ts.k.c1 * (ts.k.q - m.inv_t1b));
-            S = post ? Sp : (during ? Sd : 0.0f);
-            dSdd = post ? dp : (during ? dd : 0.0f);
+            S = post ? Sp : (arrived ? Sd : 0.0f);
+            dSdd = post ? dp : (arrived ? dd : 0.0f);
             if (WANT_Q) {
                 const float qd = FE * u - Sd * ts.k.iq;
                 const float qp = Sp * (ts.k.tc1 - u - ts.k.iq);
-                dSdq = post ? qp : (during ? qd : 0.0f);
+                dSdq = post ? qp : (arrived ? qd : 0.0f);
             }
         } else {
             // factor*(exp(r t) - exp(r delt)) = 2 exp(-t q) exp(r delt) * (exp(r u) - 1)/r, which (unlike the
@@ -223,12 +228,12 @@ struct AslRest {
             const float e1u = em1r(ts.k.r, u);
             const float Sd = Be2 * e1u;                    // aslrest.py:379
             const float Sp = Be2 * ts.k.e1tau;             // aslrest.py:380
-            S = post ? Sp : (during ? Sd : 0.0f);
-            dSdd = post ? ts.k.r * Sp : (during ? -Be2 : 0.0f);
+            S = post ? Sp : (arrived ? Sd : 0.0f);
+            dSdd = post ? ts.k.r * Sp : (arrived ? -Be2 : 0.0f);
             if (WANT_Q) {
                 const float qd = Be2 * dem1r(ts.k.r, u, e1u) - u * Sd;
                 const float qp = Be2 * ts.k.de1tau - u * Sp;
-                dSdq = post ? qp : (during ? qd : 0.0f);
+                dSdq = post ? qp : (arrived ? qd : 0.0f);
             }
         }
     }
@@ -263,13 +268,12 @@ struct AslRest {
         }
         if (ART) {
             const bool leadout = t > s.thr_out;                             // aslrest.py:411
-            const float u = t - s.deltb;
-            // z of aslrest.py:422-423 times sqrt(log2 e) (erf_step_raw) as za u + zb, lead-out: (tau - u)/leadscale
+            // z of aslrest.py:422-423 times sqrt(log2 e) (erf_step_raw): affine in t on either side of the switch
             const float za = leadout ? -m.inv_leadscale_s : s.zin_a;
-            const float zb = leadout ? m.tau_inv_leadscale_s : s.zin_b;
+            const float zb = leadout ? s.zout_b : s.zin_b;
             const float dz = leadout ? m.inv_leadscale_pi : (s.dzin_c + s.dzin_t * t);     // dz/ddeltblood / sqrt(pi)
             float h, g0;
-            erf_step_raw(za * u + zb, h, g0);
+            erf_step_raw(za * t + zb, h, g0);
             float A, dA;
             if (CASL) {                                                     // kc = 2 exp(-deltblood/t1b): per sample
                 A = h;
@@ -309,12 +313,113 @@ struct AslRest {
         return pred;
     }
 
+    // ---- CASL with a fixed T1: derivative sums without per-element derivative terms -----------------------------------
+    // For a tissue compartment  dS/ddelta = -(1/t1b - q) S - [delta < t <= delta + tau] A q   (before arrival both
+    // vanish; during the bolus S = A - F E and dS/ddelta = (1/t1b - q) F E - A/t1b; afterwards S = c1 F E and
+    // dS/ddelta = (q - 1/t1b) S), so  sum_b r_b dS_b/ddelta = -(1/t1b - q) G_f - A q (sum_{arrived} r_b - sum_{post} r_b)
+    // with G_f = sum_b r_b S_b, which the loop forms anyway; likewise the arterial term's  -h/t1b  part of
+    // dA/ddeltblood is  -G_fblood / t1b.  The time loop then only carries values, two predicated adds and the products
+    // with the residual.
+    static constexpr bool kSumForm = CASL && !T1;
+
+    struct TissueSums {
+        float f, ra, rp;          // sum_b r_b S_b; sums of r_b over the arrived / the post-bolus time points
+    };
+
+    template <bool USE_EB>
+    static SVB_HD float tissue_value(const Tissue &ts, float t, float ebt, bool &arrived, bool &post) {
+        post = t > ts.tdp;
+        arrived = t > ts.delt;
+        const float FE = USE_EB ? ts.AE * ebt : ts.A * fexp2((t - ts.delt) * ts.k.nk);
+        const float Sd = ts.A - FE;                        // aslrest.py:372
+        const float Sp = FE * ts.k.c1;                     // aslrest.py:373
+        return post ? Sp : (arrived ? Sd : 0.0f);
+    }
+
+    static SVB_HD void tissue_sums_close(const DevModel &m, const Tissue &ts, const TissueSums &u, float &G_f, float &G_d) {
+        G_f = u.f;
+        G_d = (ts.k.q - m.inv_t1b) * u.f - (ts.A * ts.k.q) * (u.ra - u.rp);
+    }
+
+    template <bool USE_EB, class Acc>
+    static SVB_HD void run_sum_form(const DevModel &m, const Vox &v, const Sample &s, Acc &acc, int b, float t,
+                                    TissueSums &ug, TissueSums &uw, float &G_fb, float &G_db) {
+        float pred = 0.0f, Sg = 0.0f, Sw = 0.0f, h = 0.0f, gdz = 0.0f;
+        bool arr_g = false, post_g = false, arr_w = false, post_w = false;
+        if (TISS) {
+            Sg = tissue_value<USE_EB>(s.gm, t, USE_EB ? v.eb[USE_EB ? b : 0] : 0.0f, arr_g, post_g);
+            pred = s.gm.pvf * Sg;
+            if (INCWM) {
+                Sw = tissue_value<USE_EB>(s.wm, t, USE_EB ? v.ebw[USE_EB ? b : 0] : 0.0f, arr_w, post_w);
+                pred += s.wm.pvf * Sw;
+            }
+        }
+        if (ART) {
+            const bool leadout = t > s.thr_out;                             // aslrest.py:411
+            const float za = leadout ? -m.inv_leadscale_s : s.zin_a;
+            const float zb = leadout ? s.zout_b : s.zin_b;
+            const float dz = leadout ? m.inv_leadscale_pi : (s.dzin_c + s.dzin_t * t);
+            float g0;
+            erf_step_raw(za * t + zb, h, g0);
+            gdz = g0 * dz;
+            pred += s.fbk * h;
+        }
+        const float r = acc.resid(b, pred);
+        if (TISS) {
+            ug.f += r * Sg;
+            if (ATT) {
+                if (arr_g) ug.ra += r;
+                if (post_g) ug.rp += r;
+            }
+            if (INCWM && INFWM) {
+                uw.f += r * Sw;
+                if (ATT) {
+                    if (arr_w) uw.ra += r;
+                    if (post_w) uw.rp += r;
+                }
+            }
+        }
+        if (ART) {
+            G_fb += r * h;
+            if (I_DELTBLOOD >= 0) G_db += r * gdz;
+        }
+    }
+
     // Visit every time point of the batch.  Acc supplies: static NB (compile-time batch size, 0 = dynamic),
-    // n(), time(b), add(b, pred, d) and the accumulated G[].
+    // n(), time(b), add(b, pred, d) / resid(b, pred) and the accumulated G[].
     template <class Acc>
     static SVB_HD void run(const DevModel &m, const Vox &v, const float *x, Acc &acc) {
         Sample s = prep_sample(m, v, x);
-        if (Acc::NB > 0) {
+        if (kSumForm) {
+            TissueSums ug = {0.0f, 0.0f, 0.0f}, uw = {0.0f, 0.0f, 0.0f};
+            float G_fb = 0.0f, G_db = 0.0f;
+            if (Acc::NB > 0) {
+#pragma unroll
+                for (int b = 0; b < (Acc::NB > 0 ? Acc::NB : 1); ++b)
+                    run_sum_form<use_eb<Acc>()>(m, v, s, acc, b, acc.time(b), ug, uw, G_fb, G_db);
+            } else {
+                const int nb = acc.n();
+                for (int b = 0; b < nb; ++b) run_sum_form<false>(m, v, s, acc, b, acc.time(b), ug, uw, G_fb, G_db);
+            }
+            float *G = acc.G;
+#pragma unroll
+            for (int p = 0; p < P; ++p) G[p] = 0.0f;             // parameters without a signal term stay at zero
+            if (TISS) {
+                float gf, gd;
+                tissue_sums_close(m, s.gm, ug, gf, gd);
+                G[ix(I_FTISS)] = gf;
+                if (ATT) G[ix(I_DELT)] = gd;
+                if (INCWM && INFWM) {
+                    tissue_sums_close(m, s.wm, uw, gf, gd);
+                    G[ix(I_FWM)] = gf;
+                    if (I_DELTWM >= 0) G[ix(I_DELTWM)] = gd;
+                }
+            }
+            if (ART) {
+                G[ix(I_FBLOOD)] = G_fb;
+                if (I_DELTBLOOD >= 0) G[ix(I_DELTBLOOD)] = G_db - m.inv_t1b * G_fb;
+            }
+        } else if (Acc::NB > 0) {
 #pragma unroll
             for (int b = 0; b < (Acc::NB > 0 ? Acc::NB : 1); ++b) {
                 float pred, d[PA];

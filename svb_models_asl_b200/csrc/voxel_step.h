@@ -10,6 +10,7 @@
 // that sits on the hot path around /root/reference/svb_models_asl/aslrest.py:248-340.  Backward-pass algebra:
 // SURVEY.md Appendix A.3 / DESIGN.md section 3.  One thread owns one voxel; nothing of size [W,S,B] ever exists.
 #pragma once
+#include <type_traits>
 #include "compat.h"
 #include "philox.h"
 #include "dev_model.h"
@@ -86,6 +87,12 @@ struct BatchAcc {
 #pragma unroll
         for (int p = 0; p < P; ++p) G[p] = 0.0f;
     }
+    // residual of time point b, accumulated into the sum of squares; the model forms its own derivative sums
+    SVB_HD float resid(int b, float pred) {
+        const float r = pred - (NBT > 0 ? y[b] : yp[b * stride]);
+        ssd += r * r;
+        return r;
+    }
     SVB_HD void add(int b, float pred, const float *d) {
         float r = pred - (NBT > 0 ? y[b] : yp[b * stride]);
         ssd += r * r;
@@ -120,6 +127,11 @@ struct NbTile {
     uint32_t mask;
 };
 
+template <class M, class = void>
+struct paired_samples : std::false_type {};
+template <class M>
+struct paired_samples<M, std::void_t<decltype(M::kPairedSamples)>> : std::bool_constant<M::kPairedSamples> {};
+
 // FL, the flavour of a step: 0 = generic (every run-time switch live); 1 = lean, the production flavour -
 // sample-based latent loss, draws from the in-register Philox stream, no spatial prior - with those three
 // switches resolved at compile time, so the hot loop carries no dead code (the generic flavour's skipped
@@ -128,7 +140,9 @@ template <class M, int NBT, int FL = 0>
 struct VoxelStep {
     static constexpr bool LEAN = FL != 0;           // numeric latent loss + Philox draws fixed at compile time
     static constexpr bool SPATIAL = FL != 1;
-    static constexpr bool PAIRED = SVB_PAIRED_SAMPLES;   // sample loop unrolled over the two samples of a Philox call
+    // sample loop unrolled over the two samples of a Philox call: for the models that ask for it (aslrest: +4.8 %; the
+    // tensor-core aslnn step loses a quarter of its rate with two copies of its pipelined row loop, profiles/r3_notes.md)
+    static constexpr bool PAIRED = SVB_PAIRED_SAMPLES && paired_samples<M>::value;
     static constexpr int P = M::P;
     static constexpr int N = P + 1;                 // noise last
     static constexpr int NL = N * (N - 1) / 2;

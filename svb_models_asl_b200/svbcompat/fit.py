@@ -163,7 +163,7 @@ class SvbFit(LogBase):
         corresponding save_* option is set).
 
         iters_per_launch: iterations fused into one kernel launch (voxel-wise priors; svbasl_adam.n_iters).  Default:
-        8, lowered to the number of batches per epoch when a per-epoch history is recorded (save_cost_history /
+        16, lowered to the number of batches per epoch when a per-epoch history is recorded (save_cost_history /
         save_param_history need the state at every epoch boundary)."""
         sample_size = sample_size or 5
         self._setup(tpts, data, batch_size, sample_size, learning_rate, epochs, **kwargs)
@@ -197,7 +197,7 @@ class SvbFit(LogBase):
         t0 = time.time()
         total = epochs * n_batches
         per_epoch = want_vc or want_ph
-        fuse = 1 if f.mrf else max(1, min(int(iters_per_launch or 8), f.max_fuse))
+        fuse = 1 if f.mrf else max(1, min(int(iters_per_launch or 16), f.max_fuse))
         done = 0
         while done < total:
             # a launch never crosses an epoch boundary at which something is recorded or displayed
