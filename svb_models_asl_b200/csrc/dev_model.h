@@ -37,6 +37,7 @@ struct TissueRates {
     float c1;             // exp(tau q) - 1 : S_post = F E c1           (aslrest.py:373, single-exp form)
     float tc1;            // tau (c1 + 1)/c1 : d log c1 / dq
     float r;              // q - 1/t1b                                  (PASL, aslrest.py:376)
+    float l2e_q_b;        // log2(e) (q - 1/t1b): exp(delta (q - 1/t1b)) = 2^(l2e_q_b delta)
     float e1tau, de1tau;  // (exp(r tau)-1)/r and its r-derivative      (PASL post-bolus, aslrest.py:380)
 };
 
@@ -46,6 +47,7 @@ SVB_HD TissueRates tissue_rates(float q, float tau, float inv_t1b, bool casl) {
     k.iq = frcp(q);
     k.nk = -1.4426950408889634f * q;
     k.two_iq = 2.0f * k.iq;
+    k.l2e_q_b = 1.4426950408889634f * (q - inv_t1b);
     k.c1 = k.tc1 = k.r = k.e1tau = k.de1tau = 0.0f;
     if (casl) {
         k.c1 = fexp(tau * q) - 1.0f;
@@ -80,6 +82,7 @@ struct DevModel {
     int32_t kind;
     uint32_t flags;
     float tau, half_tau, inv_t1b;
+    float nl2e_inv_t1b;               // -log2(e) / t1b: exp(-x / t1b) = 2^(nl2e_inv_t1b x)
     float att, attwm, fwm, artt;
     float fc_pc, fc_pc_wm;            // fcalib/pc
     float leadscale, inv_leadscale, inv_leadscale_s;   // _s: times sqrt(log2 e)
@@ -102,6 +105,7 @@ inline DevModel make_dev_model(const svbasl_model &m) {
     d.tau = m.tau;
     d.half_tau = m.tau / 2;                                            // aslrest.py:411
     d.inv_t1b = 1.0f / m.t1b;
+    d.nl2e_inv_t1b = -1.4426950408889634f * d.inv_t1b;
     d.att = m.att;
     d.attwm = m.attwm;
     d.fwm = m.fwm;

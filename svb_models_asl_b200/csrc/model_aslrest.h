@@ -155,8 +155,9 @@ struct AslRest {
             ts.k = fixed;
             ts.dqdt1 = 0.0f;
         }
-        ts.A = CASL ? ts.k.two_iq * fexp(-delt * m.inv_t1b) : 2.0f * fexp(ts.k.r * delt);
-        ts.AE = (CASL && !T1_SAMPLED) ? ts.k.two_iq * fexp(delt * (ts.k.q - m.inv_t1b)) : 0.0f;
+        // exponentials as 2^(x log2 e) with the factor folded into the rate on the host where the rate is an option
+        ts.A = CASL ? ts.k.two_iq * fexp2(delt * m.nl2e_inv_t1b) : 2.0f * fexp(ts.k.r * delt);
+        ts.AE = (CASL && !T1_SAMPLED) ? ts.k.two_iq * fexp2(delt * ts.k.l2e_q_b) : 0.0f;
         ts.Ab = CASL ? -ts.A * m.inv_t1b : 0.0f;
     }
 
@@ -177,7 +178,7 @@ struct AslRest {
             s.fb = x[ix(I_FBLOOD)];
             const float db = (I_DELTBLOOD >= 0) ? x[ix(I_DELTBLOOD)] : m.artt;
             s.deltb = db;
-            s.kc = CASL ? 2.0f * fexp(-db * m.inv_t1b) : 1.0f;
+            s.kc = CASL ? 2.0f * fexp2(db * m.nl2e_inv_t1b) : 1.0f;
             s.fbk = CASL ? s.fb * s.kc : s.fb;
             s.thr_out = db + m.half_tau;
             const float ls = fmin2(db, m.leadscale);
@@ -190,7 +191,7 @@ struct AslRest {
             // spares the time loop a select per element.
             s.zin_a = leadin_ok ? ils * SVB_SQRT_LOG2E : 0.0f;
             s.zin_b = leadin_ok ? -db * s.zin_a : -9.6f;                          // z_in = (t - deltblood) / ls
-            s.zout_b = (m.tau + db) * m.inv_leadscale_s;                          // z_out = (tau + deltblood - t) / leadscale
+            s.zout_b = db * m.inv_leadscale_s + m.tau_inv_leadscale_s;            // z_out = (tau + deltblood - t) / leadscale
             s.dzin_c = (own || !leadin_ok) ? 0.0f : -ils * SVB_INV_SQRT_PI;
             s.dzin_t = (own && leadin_ok) ? -ils * ils * SVB_INV_SQRT_PI : 0.0f;
         }

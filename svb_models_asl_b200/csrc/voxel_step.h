@@ -302,7 +302,7 @@ struct VoxelStep {
     SVB_HD float elbo_grad_batch(const DevModel &md, const svbasl_engine &e, const EngineConst &ec, int64_t w, int64_t step,
                                  typename M::Vox &vox, BatchAcc<P, NBT> &acc, const NbTile nbt = NbTile{nullptr, 0, -1, 0u}) {
         const int S = e.n_samples;
-        const float Tf = ec.t_full;
+        const float Tf = ec.t_full, half_Tf = 0.5f * ec.t_full;
         const float scale = ec.scale;
         const float lw = e.latent_weight;
         const bool numeric = LEAN || (e.latent == SVBASL_LATENT_NUMERIC);
@@ -344,12 +344,13 @@ struct VoxelStep {
 
             const float thn = th[N - 1];
             const float inv_nv = fexp(-thn);
-            const float c_ssd = scale * acc.ssd * inv_nv;
+            const float sc = scale * inv_nv;
+            const float c_ssd = sc * acc.ssd;
             cost += 0.5f * (Tf * thn + c_ssd);
             float g[N];
 #pragma unroll
-            for (int p = 0; p < P; ++p) g[p] = scale * inv_nv * acc.G[p] * dx[p];
-            g[N - 1] = 0.5f * (Tf - c_ssd);
+            for (int p = 0; p < P; ++p) g[p] = sc * acc.G[p] * dx[p];
+            g[N - 1] = half_Tf - 0.5f * c_ssd;
             if (numeric) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
