@@ -52,6 +52,9 @@ SVB_HD void erf_step_raw(float zs, float &half_1p_erf, float &g0) {
     half_1p_erf = zs >= 0.0f ? 1.0f - half_erfc : half_erfc;
 }
 #define SVB_INV_SQRT_PI 0.5641895835477563f
+#ifndef SVB_SUM_FORM
+#define SVB_SUM_FORM 1            // tuning switch (scratch/build_variant.sh): 0 = per-element derivative terms everywhere
+#endif
 
 template <uint32_t F>
 struct AslRest {
@@ -321,7 +324,7 @@ struct AslRest {
     // with G_f = sum_b r_b S_b, which the loop forms anyway; likewise the arterial term's  -h/t1b  part of
     // dA/ddeltblood is  -G_fblood / t1b.  The time loop then only carries values, two predicated adds and the products
     // with the residual.
-    static constexpr bool kSumForm = CASL && !T1;
+    static constexpr bool kSumForm = SVB_SUM_FORM && CASL && !T1;
 
     struct TissueSums {
         float f, ra, rp;          // sum_b r_b S_b; sums of r_b over the arrived / the post-bolus time points

@@ -140,9 +140,10 @@ template <class M, int NBT, int FL = 0>
 struct VoxelStep {
     static constexpr bool LEAN = FL != 0;           // numeric latent loss + Philox draws fixed at compile time
     static constexpr bool SPATIAL = FL != 1;
-    // sample loop unrolled over the two samples of a Philox call: for the models that ask for it (aslrest: +4.8 %; the
+    // sample loop unrolled over the two samples of a Philox call: for the models that ask for it, in the production
+    // flavour without the spatial prior (aslrest: +4.8 %; the spatial flavour is 7 % faster with the rolled loop, and the
     // tensor-core aslnn step loses a quarter of its rate with two copies of its pipelined row loop, profiles/r3_notes.md)
-    static constexpr bool PAIRED = SVB_PAIRED_SAMPLES && paired_samples<M>::value;
+    static constexpr bool PAIRED = SVB_PAIRED_SAMPLES && paired_samples<M>::value && FL == 1;
     static constexpr int P = M::P;
     static constexpr int N = P + 1;                 // noise last
     static constexpr int NL = N * (N - 1) / 2;
