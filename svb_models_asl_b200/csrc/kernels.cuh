@@ -131,6 +131,9 @@ template <class M>
 struct is_cta_coop<M, std::void_t<decltype(M::kCtaCoop)>> : std::bool_constant<M::kCtaCoop> {};
 
 constexpr int kMaxDeferredCosts = 16;
+#ifndef SVB_WRITE_BACK_AFTER
+#define SVB_WRITE_BACK_AFTER 1
+#endif
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -180,6 +183,10 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
     typedef VoxelStep<M, NBT, FL> VS;
     constexpr bool LEAN = FL != 0;
     constexpr bool SPATIAL = FL != 1;
+    // Production flavour without the spatial prior (the one that fuses iterations): every iteration updates the moments
+    // in their shared-memory tile and the state in registers, and ONE copy loop after the iteration loop writes both
+    // back - the iteration loop then holds a single instance of the Adam code (instruction-cache footprint).
+    constexpr bool WRITE_BACK_AFTER = SVB_WRITE_BACK_AFTER && FL == 1;
     const bool update = LEAN || a.update;
     if constexpr (is_cta_coop<M>::value) M::cta_begin(a.md);
     const int64_t local = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -267,14 +274,14 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
                 if (vs.grads_finite() && cost == cost) {
                     // the moments live in the shared-memory tile they were prefetched into for the whole launch;
                     // the last fused iteration writes them (and the state) back to global memory
-                    if (it == n_iters - 1)
+                    if (!WRITE_BACK_AFTER && it == n_iters - 1)
                         vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, true, m_sm, v_sm, kBlock, a.ad.m + w, a.ad.v + w, a.e.ld);
                     else
                         vs.adam_update(a.e, a.ad, a.ad.lr_t[step], w, false, m_sm, v_sm, kBlock, m_sm, v_sm, kBlock);
                     if (SPATIAL && it == n_iters - 1 && a.e.spatial_samples_out) vs.store_next_samples(a.e, a.ec, w, step + 1);
                 } else {
                     ++skipped;
-                    if (it == n_iters - 1) {
+                    if (!WRITE_BACK_AFTER && it == n_iters - 1) {
                         vs.store_state(a.e, w);
                         // the next iteration's samples are still due (unchanged state, new draws): the sample
                         // buffers - our own and the neighbour rank's halo columns - ping-pong every iteration
@@ -305,6 +312,14 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
             for (int i = 0; i < VS::N; ++i)
                 if (a.e.prior_type[i] == SVBASL_PRIOR_MRF)
                     block_accumulate(live ? vs.ak_out[i] : 0.0f, a.e.ak_grad + a.ec.sp_slot[i], red);
+        }
+    }
+    if (WRITE_BACK_AFTER && update && live) {
+        vs.store_state(a.e, w);
+        float *mg = a.ad.m + w, *vg = a.ad.v + w;
+        for (int k = 0; k < n_state; ++k, mg += a.e.ld, vg += a.e.ld) {
+            *mg = m_sm[k * kBlock];
+            *vg = v_sm[k * kBlock];
         }
     }
     if (cost_sum && defer_costs) {
