@@ -171,12 +171,19 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // fewer for the wide posteriors (P' >= 6: the Cholesky factor and its gradient alone are P'(P'+1) registers).
 template <class M>
 constexpr int min_blocks() {
+#ifdef SVB_MIN_BLOCKS                     // tuning builds (scratch/build_variant.sh)
+    return SVB_MIN_BLOCKS;
+#endif
     return (128 / kBlock) * (M::kRegHeavy ? 3 : (M::P + 1 <= 5 ? 4 : (M::P + 1 <= 7 ? 3 : 2)));
 }
 
 // FL != 0: production flavours - fused update, no per-voxel cost / gradient outputs (see VoxelStep)
 template <class M, int NBT, int FL>
+#ifdef SVB_MAXNREG                        // tuning builds: an explicit register cap instead of the resident-CTA hint
+__global__ void __maxnreg__(SVB_MAXNREG) step_kernel(const __grid_constant__ StepArgs a) {
+#else
 __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __grid_constant__ StepArgs a) {
+#endif
     extern __shared__ float mv_tile[];
     __shared__ float red[kBlock / 32];
     __shared__ float red_it[kMaxDeferredCosts][kBlock / 32];
