@@ -27,7 +27,6 @@ SVB_D float fsqrt(float x) {                               // sqrt.approx: MUFU.
     return y;
 }
 SVB_D float flog2(float x) { return __log2f(x); }          // MUFU.LG2
-SVB_D void fsincos2pi(float u, float *s, float *c) { __sincosf(6.283185307179586f * u, s, c); }
 SVB_D void fsincos(float x, float *s, float *c) { __sincosf(x, s, c); }     // FMUL.RZ (to turns) + MUFU.SIN + MUFU.COS
 SVB_D uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 SVB_D float ferf(float x) { return erff(x); }
@@ -49,11 +48,6 @@ SVB_HD float flog(float x) { return logf(x); }
 SVB_HD float frcp(float x) { return 1.0f / x; }
 SVB_HD float fdiv(float a, float b) { return a / b; }
 SVB_HD float fsqrt(float x) { return sqrtf(x); }
-SVB_HD void fsincos2pi(float u, float *s, float *c) {
-    float a = 6.283185307179586f * u;
-    *s = sinf(a);
-    *c = cosf(a);
-}
 SVB_HD float flog2(float x) { return log2f(x); }
 SVB_HD void fsincos(float x, float *s, float *c) {
     *s = sinf(x);

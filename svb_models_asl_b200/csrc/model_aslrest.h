@@ -16,29 +16,14 @@
 
 namespace svb {
 
-// 1/2 (1 + erf z) and exp(-z^2)/sqrt(pi) together, branch-free, from ONE exponential:
+// 1/2 (1 + erf z) and exp(-z^2) together, branch-free, from ONE exponential:
 // erfc(|z|) = (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p|z|)  (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7),
 // so the smoothed step is accurate to 7.5e-8 absolute - below float32 resolution of values near 1.
 // The argument arrives pre-scaled, zs = z*sqrt(log2 e), so that exp(-z^2) = 2^(-zs^2) is one FMUL + MUFU.EX2;
 // |zs| is clamped at 9.6 (|z| = 8, erfc ~ 1e-29) to keep the exponential a normal number.  The polynomial
-// coefficients carry the factor 1/2 of the half-step.
+// coefficients carry the factor 1/2 of the half-step; the Gaussian's constant 1/sqrt(pi) is left to the caller, who
+// folds it into its own factors.
 #define SVB_SQRT_LOG2E 1.2011224087864498f
-SVB_HD void erf_step_scaled(float zs, float &half_1p_erf, float &gauss) {
-    const float a = fmin2(fabsf(zs), 9.6f);
-    const float t = frcp(1.0f + (0.3275911f / SVB_SQRT_LOG2E) * a);
-    float p = 0.5f * 1.061405429f;
-    p = p * t - 0.5f * 1.453152027f;
-    p = p * t + 0.5f * 1.421413741f;
-    p = p * t - 0.5f * 0.284496736f;
-    p = p * t + 0.5f * 0.254829592f;
-    const float g0 = fexp2(-a * a);
-    const float half_erfc = (p * t) * g0;
-    half_1p_erf = zs >= 0.0f ? 1.0f - half_erfc : half_erfc;
-    gauss = 0.5641895835477563f * g0;
-}
-
-// The same step for callers that fold the Gaussian's constant 1/sqrt(pi) into their own factors: returns
-// 1/2 (1 + erf z) and the bare exp(-z^2).
 SVB_HD void erf_step_raw(float zs, float &half_1p_erf, float &g0) {
     const float a = fmin2(fabsf(zs), 9.6f);
     const float t = frcp(1.0f + (0.3275911f / SVB_SQRT_LOG2E) * a);
@@ -129,7 +114,7 @@ struct AslRest {
         // arterial (aslrest.py:404-419).  The time loop produces RAW terms: for CASL the per-sample factor
         // kc = 2 exp(-deltblood/t1b) is applied after the loop (fbk = fblood kc on the prediction, scale_grads on the
         // derivative sums); the Gaussian's 1/sqrt(pi) sits in the dz factors.
-        float fb, fbk, deltb, kc;
+        float fb, fbk, kc;
         float thr_out;            // lead-out begins at deltblood + tau/2                         (aslrest.py:411)
         float zin_a, zin_b;       // lead-in:  z sqrt(log2 e) = zin_a t + zin_b                   (aslrest.py:413-423)
         float zout_b;             // lead-out: z sqrt(log2 e) = -t/leadscale' + zout_b            (aslrest.py:412,422)
@@ -180,7 +165,6 @@ struct AslRest {
         if (ART) {
             s.fb = x[ix(I_FBLOOD)];
             const float db = (I_DELTBLOOD >= 0) ? x[ix(I_DELTBLOOD)] : m.artt;
-            s.deltb = db;
             s.kc = CASL ? 2.0f * fexp2(db * m.nl2e_inv_t1b) : 1.0f;
             s.fbk = CASL ? s.fb * s.kc : s.fb;
             s.thr_out = db + m.half_tau;

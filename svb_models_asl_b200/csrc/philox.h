@@ -30,10 +30,6 @@ SVB_HD uint32_t rng_key(uint64_t seed, int64_t step) {
            ((uint32_t)((uint64_t)step >> 32) * 0xC2B2AE3Du);
 }
 
-// uniform in (0,1): 24 random bits, never 0 or 1 (slow paths and tests; the Box-Muller pair below converts the full
-// 32-bit words itself)
-SVB_HD float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f + 2.98023223876953125e-08f; }
-
 // Box-Muller pair from two 32-bit words in 12 instructions: u = (x + 1/2) 2^-32 straight from the unsigned-to-float
 // conversion (one I2FP + one FFMA per word; the conversion rounds to nearest, so u lies in [2^-33, 1] and the
 // radius in [0, 6.8]), the radius as sqrt(-2 ln2 * lg2 u) (MUFU.LG2, FMUL, MUFU.SQRT) and the angle with 2 pi

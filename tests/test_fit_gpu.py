@@ -111,8 +111,11 @@ def test_fused_iterations_equal_single_iterations():
     rng = np.random.default_rng(3)
     vol, _f, _d = _sim_volume((4, 8, 9), rng, repeats=8, slicedt=0.0452)
     data = vol.reshape(-1, 48)
-    states, moments = [], []
-    for fuse in (1, 8):
+    # 8 and 16 per launch: the per-iteration cost sums leave the CTA after the iteration loop; 24: more than the kernel
+    # defers (kMaxDeferredCosts), reduced inside the loop; state and moments are written back once per launch in all
+    states, moments, cost_hists = [], [], []
+    n_total = 48
+    for fuse in (1, 8, 16, 24):
         dm = DataModel(data)
         model = AslRestModel(dm, tau=1.8, casl=True, plds=PLDS, repeats=[8], slicedt=0.0452, inferart=True)
         fit = SvbFit(dm, model)
@@ -122,18 +125,22 @@ def test_fused_iterations_equal_single_iterations():
         # after the posterior initialisation (which reads the data): non-finite samples in the device copy
         f.data[3, 5] = float("nan")         # a voxel whose update is skipped in every iteration that sees row 3
         f.data[7, 9] = float("nan")         # ... and one skipped in the LAST iteration of each fused launch
-        for _ in range(16 // fuse):
+        for _ in range(n_total // fuse):
             f.step(fuse)
-        assert f.step_count == 16
+        assert f.step_count == n_total
         states.append(f.state.cpu().numpy())
         moments.append((f.m.cpu().numpy(), f.v.cpu().numpy()))
-        costs = f.cost_hist[:16].cpu().numpy()
+        costs = f.cost_hist[:n_total].cpu().numpy()
         assert np.isfinite(costs).all() and (costs != 0).all()
-        assert int(f.nan_count.item()) == 4                    # 16 iterations over 8 strided batches: each row twice
-    np.testing.assert_array_equal(states[0], states[1])
-    # the Adam moments stay in shared memory between fused iterations and must come back identical
-    np.testing.assert_array_equal(moments[0][0], moments[1][0])
-    np.testing.assert_array_equal(moments[0][1], moments[1][1])
+        cost_hists.append(costs)
+        assert int(f.nan_count.item()) == 12                   # 48 iterations over 8 strided batches: each row six times
+    for k in range(1, len(states)):
+        np.testing.assert_array_equal(states[0], states[k])
+        # the Adam moments stay in shared memory between fused iterations and must come back identical
+        np.testing.assert_array_equal(moments[0][0], moments[k][0])
+        np.testing.assert_array_equal(moments[0][1], moments[k][1])
+        # per-iteration cost sums: the same per-CTA floats, added in double by atomics (order across CTAs is free)
+        np.testing.assert_allclose(cost_hists[0], cost_hists[k], rtol=1e-12)
     assert np.isfinite(states[0]).all()
 
 
