@@ -535,6 +535,10 @@ def main():
     ap.add_argument("--c5-max-iters", type=int, default=20000)
     ap.add_argument("--no-shard-parity", action="store_true")
     ap.add_argument("--only-c5", action="store_true", help="run the c5_strong (+ shard_parity) leg alone (our own sweeps)")
+    ap.add_argument("--sweep-env", default=None,
+                    help="our own tuning sweeps: 'NAME=v1,v2;NAME2=w1,w2' - times the workload's launches under every "
+                         "combination of these environment switches of the library (read per launch), prints a table to "
+                         "stderr and exits")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, out)
@@ -617,6 +621,20 @@ def main():
     step_fn = (lambda: f.step(ipl)) if not f.mrf else f.step
     for _ in range(WU):
         step_fn()
+    if args.sweep_env:
+        import itertools
+        axes = [(kv.split("=")[0], kv.split("=")[1].split(",")) for kv in args.sweep_env.split(";") if kv]
+        for combo in itertools.product(*[v for _k, v in axes]):
+            for (k, _v), val in zip(axes, combo):
+                os.environ[k] = val
+            for _ in range(2):
+                step_fn()
+            ms, _per = timed_steps(D, torch, step_fn, K)
+            if rank == 0:
+                sys.stderr.write("sweep %s: %.4f ms per launch, %.4g voxel-iters/s\n"
+                                 % (" ".join("%s=%s" % (k, v) for (k, _), v in zip(axes, combo)), ms / K,
+                                    W_total * K * ipl / (ms * 1e-3)))
+        return
     sampler = ClockSampler(local_rank).start()
     total_ms, per_launch_ms = timed_steps(D, torch, step_fn, K)
     clocks_k = sampler.stop()
