@@ -311,6 +311,11 @@ def test_rng_stream_is_sharding_invariant_and_normal(be):
     x = a.ravel()
     assert abs(x.mean()) < 0.02 and abs(x.std() - 1) < 0.02
     assert abs((x ** 3).mean()) < 0.05 and abs((x ** 4).mean() - 3) < 0.15
+    # the whole distribution, not only its moments (Box-Muller from the full 32-bit Philox words, philox.h): Kolmogorov
+    # distance to the normal CDF below the 0.1 % critical value 1.95 / sqrt(n), and the tails where they belong
+    from scipy import stats
+    assert stats.kstest(x, "norm").statistic < 1.95 / np.sqrt(x.size)
+    assert abs((np.abs(x) > 3).mean() - 0.0027) < 0.0006 and np.abs(x).max() < 6.8
     # independence across parameters / samples of one voxel
     flat = a.reshape(P * S, W)
     cc = np.corrcoef(flat)
