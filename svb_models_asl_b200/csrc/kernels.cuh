@@ -230,24 +230,25 @@ __global__ void __launch_bounds__(kBlock, min_blocks<M>()) step_kernel(const __g
             cp_async4(dv, vg);
         }
     }
-    NbTile nbt = {nullptr, 0, -1, 0u};
+    NbTile nbt = {nullptr, 0, -1};
     if (tile) {
         const size_t off = update ? 2 * (size_t)n_state * kBlock : 0;
         const int S = a.e.n_samples;
         const float *src = a.e.spatial_samples + (int64_t)a.ec.sp_slot[a.nb_param] * S * a.e.ld;
         unsigned dst = sm0 + (unsigned)off * 4u;
-        uint32_t mask = 0;
+        // A missing neighbour (volume edge, masked-out voxel) is replaced by the voxel ITSELF: the buffer holds the
+        // voxel's own sample of this iteration too - the very value the sample loop computes for theta (bit for bit for
+        // the first parameter, to rounding otherwise) - so its difference term vanishes and neither the copies nor the
+        // sample loop test a mask.
 #pragma unroll
-        for (int k = 0; k < 6; ++k) mask |= (nb_u[k] >= 0 ? 1u : 0u) << k;
+        for (int k = 0; k < 6; ++k) nb_u[k] = nb_u[k] >= 0 ? nb_u[k] : (int)w;
         for (int s = 0; s < S; ++s, src += a.e.ld, dst += 6u * kRow) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k)
-                if ((mask >> k) & 1u) cp_async4(dst + k * kRow, src + nb_u[k]);
+            for (int k = 0; k < 6; ++k) cp_async4(dst + k * kRow, src + nb_u[k]);
         }
         nbt.v = mv_tile + off + threadIdx.x;
         nbt.stride = kBlock;
         nbt.param = a.nb_param;
-        nbt.mask = mask;
     }
     const int n_iters = update ? a.ad.n_iters : 1;
     // the per-iteration cost sums of a fused launch leave the CTA together after the last iteration: no CTA barrier

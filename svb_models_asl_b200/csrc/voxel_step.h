@@ -118,13 +118,13 @@ SVB_HD float sample_theta(const svbasl_engine &e, uint32_t key, int64_t u, int p
 }
 
 // The neighbours' samples of ONE spatial parameter, staged per thread (kernels.cuh copies them into shared memory
-// asynchronously at kernel start): v[(s*6 + k) * stride] = sample s of neighbour k, mask bit k = neighbour exists.
+// asynchronously at kernel start): v[(s*6 + k) * stride] = sample s of neighbour k; a neighbour that does not exist is
+// represented by the voxel's own sample (zero difference).
 // v == nullptr: no tile, elbo_grad gathers from e.spatial_samples where it needs them.
 struct NbTile {
     const float *v;
     int stride;
     int param;
-    uint32_t mask;
 };
 
 template <class M, class = void>
@@ -290,7 +290,7 @@ struct VoxelStep {
 
     // Cost of this voxel for one batch, gradients left in g_*.  Returns the un-scaled cost.
     SVB_HD float elbo_grad(const DevModel &md, const svbasl_engine &e, const EngineConst &ec, int64_t w, int64_t step,
-                           int row0, const NbTile nbt = NbTile{nullptr, 0, -1, 0u}) {
+                           int row0, const NbTile nbt = NbTile{nullptr, 0, -1}) {
         typename M::Vox vox = M::load_vox(md, w);
         BatchAcc<P, NBT> acc;
         acc.load(e, w, row0);
@@ -301,7 +301,7 @@ struct VoxelStep {
     // The same with the batch (data, time points, per-time-point model constants) already loaded: the iterations fused
     // into one launch share it when every iteration sees the same batch (n_batches == 1).
     SVB_HD float elbo_grad_batch(const DevModel &md, const svbasl_engine &e, const EngineConst &ec, int64_t w, int64_t step,
-                                 typename M::Vox &vox, BatchAcc<P, NBT> &acc, const NbTile nbt = NbTile{nullptr, 0, -1, 0u}) {
+                                 typename M::Vox &vox, BatchAcc<P, NBT> &acc, const NbTile nbt = NbTile{nullptr, 0, -1}) {
         const int S = e.n_samples;
         const float Tf = ec.t_full, half_Tf = 0.5f * ec.t_full;
         const float scale = ec.scale;
@@ -368,11 +368,9 @@ struct VoxelStep {
                             const float *nv = nbt.v + (int64_t)s * 6 * nbt.stride;
 #pragma unroll
                             for (int nbr = 0; nbr < 6; ++nbr) {
-                                if ((nbt.mask >> nbr) & 1u) {
-                                    const float dxu = th[i] - nv[nbr * nbt.stride];
-                                    sdx += dxu;
-                                    sdx2 += dxu * dxu;
-                                }
+                                const float dxu = th[i] - nv[nbr * nbt.stride];
+                                sdx += dxu;
+                                sdx2 += dxu * dxu;
                             }
                         } else {
 #pragma unroll

@@ -26,7 +26,7 @@ static int run_step(const svbasl_model *md, const svbasl_engine *e, const svbasl
         const int64_t w = e->w_begin + local;
         VoxelStep<M, NBT, FL> vs;
         vs.load(*e, w);
-        NbTile nbt = {nullptr, 0, -1, 0u};
+        NbTile nbt = {nullptr, 0, -1};
         std::vector<float> tile;
         if (FL == 2) {
             for (int i = 0; i < e->n_par && nbt.param < 0; ++i)
@@ -36,9 +36,8 @@ static int run_step(const svbasl_model *md, const svbasl_engine *e, const svbasl
                 tile.assign((size_t)6 * S, 0.0f);
                 const float *src = e->spatial_samples + (int64_t)ec.sp_slot[nbt.param] * S * e->ld;
                 for (int k = 0; k < 6; ++k) {
-                    const int u = e->neighbours[(int64_t)k * e->ld + w];
-                    if (u < 0) continue;
-                    nbt.mask |= 1u << k;
+                    int u = e->neighbours[(int64_t)k * e->ld + w];
+                    if (u < 0) u = (int)w;                       // a missing neighbour is the voxel itself: zero difference
                     for (int sidx = 0; sidx < S; ++sidx) tile[(size_t)sidx * 6 + k] = src[(int64_t)sidx * e->ld + u];
                 }
                 nbt.v = tile.data();
