@@ -37,7 +37,8 @@ def cfg_flags(cfg):
 class Backend:
     """Owns buffers on the right side (numpy for hostsim, torch.cuda for cuda) and calls the library."""
 
-    def __init__(self, kind):
+    def __init__(self, kind, defines=()):
+        """defines: hostsim only - a variant build of the device headers (tests/hostsim/build_hostsim.py)."""
         self.kind = kind
         self.keep = []
         if kind == "cuda":
@@ -45,7 +46,7 @@ class Backend:
             self.dev = torch.device("cuda:0")
         else:
             from tests.hostsim.build_hostsim import build
-            self.lib = C.CDLL(build())
+            self.lib = C.CDLL(build(tuple(defines)))
             self.lib.hostsim_step.argtypes = [C.POINTER(L.Model), C.POINTER(L.Engine), C.POINTER(L.Adam), C.c_int64,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
             self.lib.hostsim_evaluate.argtypes = [C.POINTER(L.Model), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

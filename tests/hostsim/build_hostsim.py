@@ -13,9 +13,13 @@ LIB = os.path.join(OUT, "libhostsim.so")
 sys.path.insert(0, ROOT)
 
 
-def build():
+def build(defines=()):
+    """defines: extra -D switches of the device headers (e.g. ("SVB_SUM_FORM=0",)): a variant library beside the
+    default one, for tests that compare two formulations of the same arithmetic."""
     from svb_models_asl_b200.build import aslrest_flag_sets, disp_flag_sets, variants
     os.makedirs(OUT, exist_ok=True)
+    tag = "".join("_" + d.replace("=", "").lower() for d in defines)
+    lib = os.path.join(OUT, "libhostsim%s.so" % tag)
     flags = aslrest_flag_sets()
     fast = sorted({(f, nbt) for (_m, kind, f, nbt, _l, _e) in variants() if kind == 0 and nbt})
     hdr = ["// GENERATED", "#define HOSTSIM_ASLREST_FLAGS " + " ".join("X(0x%xu)" % f for f in flags),
@@ -31,16 +35,17 @@ def build():
     h = hashlib.sha256()
     for s in srcs:
         h.update(open(s, "rb").read())
-    stamp = os.path.join(OUT, "digest.txt")
-    if os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
-        return LIB
-    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I", CSRC, "-I", OUT,
-           os.path.join(HERE, "hostsim.cpp"), "-o", LIB]
+    h.update(" ".join(defines).encode())
+    stamp = os.path.join(OUT, "digest%s.txt" % tag)
+    if os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == h.hexdigest():
+        return lib
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I", CSRC, "-I", OUT] + \
+          ["-D" + d for d in defines] + [os.path.join(HERE, "hostsim.cpp"), "-o", lib]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("hostsim build failed:\n" + res.stderr[-6000:])
     open(stamp, "w").write(h.hexdigest())
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
